@@ -1,0 +1,194 @@
+/*
+ * prt.h -- C ABI of the B200 path-tracing core (libprt.so).
+ *
+ * This is the drop-in boundary for pyrenderer's render loop.  The reference
+ * (sontung/pyrenderer) has NO FFI: its boundary is the Python object protocol
+ * consumed by main.py / main_taichi.py.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root); the
+ * Python side of the boundary (pyrenderer_b200/_abi.py + core/, io_utils/)
+ * binds these with ctypes -- see INTEGRATION.md for the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *  - every function returns PRT_OK (0) or a negative prt_status; nothing
+ *    throws or aborts across the ABI; prt_last_error() gives the text.
+ *  - "_dev" pointers are device memory owned by the CALLER (e.g. a torch
+ *    tensor's data_ptr()); the library owns the scene, the BVH and the
+ *    wavefront queues.  "_host" pointers are ordinary host memory.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *    Calls are stream-ordered and asynchronous unless stated otherwise.
+ *  - one context per device; a context is not thread-safe, distinct contexts
+ *    are independent.
+ *  - there is no CPU fallback: without a CUDA device prt_create fails.
+ */
+#ifndef PRT_H
+#define PRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRT_ABI_VERSION 1
+
+typedef struct prt_ctx prt_ctx;
+
+typedef enum {
+    PRT_OK = 0,
+    PRT_ERR_INVALID = -1, /* bad argument */
+    PRT_ERR_CUDA = -2,    /* CUDA runtime error (text in prt_last_error) */
+    PRT_ERR_STATE = -3,   /* call order: e.g. trace before bvh build */
+    PRT_ERR_NOMEM = -4
+} prt_status;
+
+/* material types: core/bsdf.py:18-65 (lambert, null) and
+ * core/bsdf_taichi.py:45-86 (Metal -> mirror/conductor, Dielectric) */
+enum { PRT_MAT_LAMBERT = 0, PRT_MAT_EMITTER = 1, PRT_MAT_MIRROR = 2, PRT_MAT_DIELECTRIC = 3,
+       PRT_MAT_CONDUCTOR = 4 };
+
+typedef struct {
+    float albedo[3];    /* BSDF*.rho / Materials.colors */
+    uint32_t type;      /* PRT_MAT_* */
+    float ior;          /* dielectric */
+    float roughness;    /* conductor fuzz, bsdf_taichi.py:49 */
+    uint32_t two_sided; /* 1 == reference `sided == 0` (normal flips to face the ray) */
+    uint32_t pad;
+} prt_material; /* 32 bytes */
+
+/* ray record: 2 x float4.  Replaces core/ray.py:5-17 (position, direction,
+ * bounds[0], bounds[1]). */
+typedef struct {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, tmax;
+} prt_ray; /* 32 bytes */
+
+/* hit record: replaces the dict {"hit","t","position",...} of
+ * mathematics/intersection.py:106-116.  tri == -1 is a miss; tri is the
+ * GLOBAL triangle id (core/scene.py:40-46 merged face order); (u,v) are the
+ * Moller-Trumbore barycentrics of p1 and p2. */
+typedef struct {
+    float t, u, v;
+    int32_t tri;
+} prt_hit; /* 16 bytes */
+
+/* camera: core/camera.py:14-25,41-72.  iview is row-major in the reference's
+ * row-vector convention (world = [x y z 1] @ iview). */
+typedef struct {
+    double iview[16];
+    double sensor_w; /* tan(radians(fov)/2) * focal * aspect */
+    double sensor_h; /* tan(radians(fov)/2) * focal */
+    double focal;
+    uint32_t width, height;
+} prt_camera;
+
+typedef struct {
+    uint64_t seed;        /* Philox key */
+    uint32_t spp_begin;   /* samples [spp_begin, spp_end) of every pixel */
+    uint32_t spp_end;
+    uint32_t max_depth;   /* PathTracer(depth) core/tracing.py:48 */
+    uint32_t rr_start;    /* first bounce with Russian roulette; 0xffffffff = off (reference) */
+    float light_color[3]; /* core/tracing.py:120 */
+    float tmin, tmax;     /* core/tracing.py:127 */
+    uint32_t flags;       /* reserved, 0 */
+} prt_render_params;
+
+typedef struct {
+    uint32_t n_tris, n_nodes, depth, max_leaf_tris;
+    float sah_cost;
+    float ms_total, ms_morton, ms_sort, ms_hierarchy, ms_refit, ms_emit;
+} prt_bvh_stats;
+
+typedef struct {
+    uint64_t rays_closest, rays_shadow; /* rays traced since the last reset */
+    uint64_t node_visits, tri_tests;    /* only counted by PRT_TRACE_COUNT launches */
+    uint64_t flagged_rays;              /* rays re-resolved in FP64 by PRT_TRACE_EXACT */
+    uint64_t paths;
+} prt_counters;
+
+/* trace flags */
+#define PRT_TRACE_EXACT 1u /* FP32 pass flags low-margin decisions, FP64 replay of the
+                              reference's Moller-Trumbore resolves them (bit-exact ids) */
+#define PRT_TRACE_COUNT 2u /* counter-instrumented twin kernel (roofline N_node / N_tri) */
+#define PRT_TRACE_BRUTE 4u /* ignore the BVH: test every triangle (Aggregator semantics,
+                              accelerators/aggregator.py:74-85) */
+
+/* BVH build options */
+typedef struct {
+    uint32_t max_leaf_tris; /* 1..7, default 4 */
+    float cost_node;        /* SAH traversal cost, default 1.0 */
+    float cost_tri;         /* SAH intersection cost, default 1.0 */
+    uint32_t rotations;     /* 1 = SAH tree rotations during refit (default 1) */
+} prt_bvh_options;
+
+int prt_abi_version(void);
+
+/* lifetime.  Replaces: ti.init(arch=ti.gpu) main_taichi.py:12 + World() :41 */
+int prt_create(int device, prt_ctx** out);
+void prt_destroy(prt_ctx* ctx);
+/* text of the last error on this context (ctx == NULL: last prt_create error) */
+const char* prt_last_error(const prt_ctx* ctx);
+
+/* scene upload (host pointers).  Replaces Scene.add_primitive core/scene.py:31-46
+ * + World.add/commit mathematics/intersection_taichi.py:220-233.
+ *   verts      [nt][3][3] f32, global triangle-id order
+ *   normals    [nt][3] f32 geometric normals with the reference's sign convention
+ *              (mathematics/shapes.py:43-47,172-176); NULL = +normalize(e1 x e2)
+ *   tri_material [nt] index into mats; NULL = all 0
+ *   light_tris [nl] triangle ids that NEE samples (Scene.lights) */
+int prt_scene_set_triangles(prt_ctx* ctx, const float* verts_host, const float* normals_host,
+                            uint32_t nt, const uint32_t* tri_material_host,
+                            const prt_material* mats_host, uint32_t nm,
+                            const uint32_t* light_tris_host, uint32_t nl);
+/* same, geometry already on the device (large soups); one default Lambert material */
+int prt_scene_set_triangles_dev(prt_ctx* ctx, const float* verts_dev, uint32_t nt, void* stream);
+
+/* GPU LBVH build.  Replaces BVH.build accelerators/bvh.py:192-215 and
+ * Aggregator.push/update accelerators/aggregator.py:25-72 and
+ * accelerators/bvh_taichi.py:111-161.  Synchronous.  opts/stats may be NULL. */
+int prt_bvh_build(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats);
+
+/* camera.  Replaces Camera.__init__/convert_to_taichi_camera core/camera.py:14-36 */
+int prt_camera_set(prt_ctx* ctx, const prt_camera* cam);
+
+/* primary rays for samples [s0,s1) of every pixel, written as
+ * rays_dev[(pixel*(s1-s0) + s-s0)]; jitter=0 -> pixel centres.
+ * Replaces Camera.generate_ray core/camera.py:41-72 under main.py:31-33. */
+int prt_generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int jitter,
+                      float tmin, float tmax, prt_ray* rays_dev, void* stream);
+
+/* closest hit.  Replaces Scene.hit/hit_faster core/scene.py:59-73,
+ * BVH.hit accelerators/bvh.py:218-237, World.hit_all
+ * mathematics/intersection_taichi.py:238-291. */
+int prt_trace_closest(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, prt_hit* hits_dev,
+                      uint32_t flags, void* stream);
+/* any hit in [tmin,tmax] (shadow rays, core/tracing.py:101-102): occluded_dev[i] = 0/1 */
+int prt_trace_any(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, uint8_t* occluded_dev,
+                  uint32_t flags, void* stream);
+/* full hit set per ray: count and order-free checksum sum((id+1)*0x9E3779B97F4A7C15) */
+int prt_trace_all(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, uint32_t* counts_dev,
+                  uint64_t* sums_dev, uint32_t flags, void* stream);
+/* closest hit with HOST buffers (copies in and out inside the call; synchronous) */
+int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n,
+                           prt_hit* hits_host, uint32_t flags);
+
+/* render.  Replaces the pixel x spp loop of main.py:28-55 around
+ * path_tracing(), and render() main_taichi.py:80-99 + PathTracer.trace
+ * core/tracing.py:116-155.  ADDS samples [spp_begin, spp_end) of every pixel to
+ * accum_dev [h][w][4] f32 (r,g,b sums, sample count); row 0 is v = 0 (bottom).
+ * prim_ids_dev (optional) [h][w][spp_end-spp_begin] i32 primary-hit triangle ids. */
+int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev,
+               int32_t* prim_ids_dev, void* stream);
+/* same with a HOST accumulation buffer (upload, render, download; synchronous) */
+int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
+/* paths per wavefront wave (default 4 Mi); 0 keeps the current value */
+int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths);
+
+int prt_get_counters(prt_ctx* ctx, prt_counters* out); /* synchronous */
+int prt_reset_counters(prt_ctx* ctx);
+int prt_synchronize(prt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRT_H */

@@ -1,0 +1,249 @@
+"""ctypes binding of libprt.so (include/prt.h).
+
+This is the only place the Python side touches the native library.  There is
+no CPU fallback: if the library is missing it is built with nvcc, and if that
+fails -- or no B200 is present when a context is created -- an error is raised.
+PyTorch appears only as the owner of device buffers (``tensor.data_ptr()``).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+MATERIAL_DTYPE = np.dtype(
+    [("albedo", "<f4", 3), ("type", "<u4"), ("ior", "<f4"), ("roughness", "<f4"),
+     ("two_sided", "<u4"), ("pad", "<u4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
+
+TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE = 1, 2, 4
+
+
+class PrtCamera(C.Structure):
+    _fields_ = [("iview", C.c_double * 16), ("sensor_w", C.c_double), ("sensor_h", C.c_double),
+                ("focal", C.c_double), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class PrtRenderParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("spp_begin", C.c_uint32), ("spp_end", C.c_uint32),
+                ("max_depth", C.c_uint32), ("rr_start", C.c_uint32),
+                ("light_color", C.c_float * 3), ("tmin", C.c_float), ("tmax", C.c_float),
+                ("flags", C.c_uint32)]
+
+
+class PrtBvhStats(C.Structure):
+    _fields_ = [("n_tris", C.c_uint32), ("n_nodes", C.c_uint32), ("depth", C.c_uint32),
+                ("max_leaf_tris", C.c_uint32), ("sah_cost", C.c_float), ("ms_total", C.c_float),
+                ("ms_morton", C.c_float), ("ms_sort", C.c_float), ("ms_hierarchy", C.c_float),
+                ("ms_refit", C.c_float), ("ms_emit", C.c_float)]
+
+
+class PrtBvhOptions(C.Structure):
+    _fields_ = [("max_leaf_tris", C.c_uint32), ("cost_node", C.c_float), ("cost_tri", C.c_float),
+                ("rotations", C.c_uint32)]
+
+
+class PrtCounters(C.Structure):
+    _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("flagged_rays", C.c_uint64), ("paths", C.c_uint64)]
+
+
+EXPORTS = [
+    "prt_abi_version", "prt_create", "prt_destroy", "prt_last_error", "prt_scene_set_triangles",
+    "prt_scene_set_triangles_dev", "prt_bvh_build", "prt_camera_set", "prt_generate_rays",
+    "prt_trace_closest", "prt_trace_any", "prt_trace_all", "prt_trace_closest_host", "prt_render",
+    "prt_render_host", "prt_set_wave_paths", "prt_get_counters", "prt_reset_counters",
+    "prt_synchronize",
+]
+
+
+class PrtError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building if needed) libprt.so.  Raises if it cannot be produced."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.build()
+    lib = C.CDLL(path)
+    vp, u32, u64, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float
+    lib.prt_abi_version.restype = C.c_int
+    lib.prt_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.prt_destroy.argtypes = [vp]
+    lib.prt_destroy.restype = None
+    lib.prt_last_error.argtypes = [vp]
+    lib.prt_last_error.restype = C.c_char_p
+    lib.prt_scene_set_triangles.argtypes = [vp, vp, vp, u32, vp, vp, u32, vp, u32]
+    lib.prt_scene_set_triangles_dev.argtypes = [vp, vp, u32, vp]
+    lib.prt_bvh_build.argtypes = [vp, C.POINTER(PrtBvhOptions), C.POINTER(PrtBvhStats)]
+    lib.prt_camera_set.argtypes = [vp, C.POINTER(PrtCamera)]
+    lib.prt_generate_rays.argtypes = [vp, u64, u32, u32, C.c_int, f32, f32, vp, vp]
+    lib.prt_trace_closest.argtypes = [vp, vp, u64, vp, u32, vp]
+    lib.prt_trace_any.argtypes = [vp, vp, u64, vp, u32, vp]
+    lib.prt_trace_all.argtypes = [vp, vp, u64, vp, vp, u32, vp]
+    lib.prt_trace_closest_host.argtypes = [vp, vp, u64, vp, u32]
+    lib.prt_render.argtypes = [vp, C.POINTER(PrtRenderParams), vp, vp, vp]
+    lib.prt_render_host.argtypes = [vp, C.POINTER(PrtRenderParams), vp]
+    lib.prt_set_wave_paths.argtypes = [vp, u64]
+    lib.prt_get_counters.argtypes = [vp, C.POINTER(PrtCounters)]
+    lib.prt_reset_counters.argtypes = [vp]
+    lib.prt_synchronize.argtypes = [vp]
+    for name in EXPORTS:
+        if name not in ("prt_destroy", "prt_last_error"):
+            getattr(lib, name).restype = C.c_int
+    if lib.prt_abi_version() != 1:
+        raise PrtError("libprt.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor (or int address) -> void*"""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if not t.is_cuda or not t.is_contiguous():
+        raise PrtError("device buffers must be contiguous CUDA tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(getattr(stream, "cuda_stream", stream))
+
+
+class Context:
+    """One device context (prt_create .. prt_destroy)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.prt_create(int(device), C.byref(h))
+        if rc != 0:
+            raise PrtError(self.lib.prt_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.prt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PrtError(f"[{rc}] " + self.lib.prt_last_error(self.h).decode())
+
+    # -- scene ---------------------------------------------------------------
+    def set_triangles(self, verts, normals=None, tri_material=None, materials=None, light_tris=None):
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
+        nt = verts.shape[0]
+        normals = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(nt, 3)
+        tri_material = None if tri_material is None else np.ascontiguousarray(tri_material, np.uint32)
+        materials = None if materials is None else np.ascontiguousarray(materials, MATERIAL_DTYPE)
+        light_tris = np.zeros(0, np.uint32) if light_tris is None else np.ascontiguousarray(light_tris, np.uint32)
+        self._check(self.lib.prt_scene_set_triangles(
+            self.h, _np_ptr(verts), _np_ptr(normals), nt, _np_ptr(tri_material), _np_ptr(materials),
+            0 if materials is None else materials.shape[0], _np_ptr(light_tris), light_tris.shape[0]))
+
+    def set_triangles_dev(self, verts_dev, nt, stream=None):
+        self._check(self.lib.prt_scene_set_triangles_dev(self.h, _dev_ptr(verts_dev), int(nt),
+                                                         _stream_ptr(stream)))
+
+    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=1.0, rotations=1):
+        opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations))
+        st = PrtBvhStats()
+        self._check(self.lib.prt_bvh_build(self.h, C.byref(opts), C.byref(st)))
+        return {k: getattr(st, k) for k, _ in PrtBvhStats._fields_}
+
+    def set_camera(self, iview, sensor_w, sensor_h, focal, width, height):
+        cam = PrtCamera()
+        iv = np.ascontiguousarray(iview, np.float64).reshape(16)
+        for i in range(16):
+            cam.iview[i] = float(iv[i])
+        cam.sensor_w, cam.sensor_h, cam.focal = float(sensor_w), float(sensor_h), float(focal)
+        cam.width, cam.height = int(width), int(height)
+        self._check(self.lib.prt_camera_set(self.h, C.byref(cam)))
+        self.resolution = (int(width), int(height))
+
+    # -- tracing ---------------------------------------------------------------
+    def generate_rays(self, rays_dev, seed=0, s0=0, s1=1, jitter=False, tmin=1e-5, tmax=99999.9,
+                      stream=None):
+        self._check(self.lib.prt_generate_rays(self.h, int(seed), int(s0), int(s1), 1 if jitter else 0,
+                                               float(tmin), float(tmax), _dev_ptr(rays_dev),
+                                               _stream_ptr(stream)))
+
+    def trace_closest(self, rays_dev, n, hits_dev, flags=0, stream=None):
+        self._check(self.lib.prt_trace_closest(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(hits_dev),
+                                               int(flags), _stream_ptr(stream)))
+
+    def trace_any(self, rays_dev, n, occluded_dev, flags=0, stream=None):
+        self._check(self.lib.prt_trace_any(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(occluded_dev),
+                                           int(flags), _stream_ptr(stream)))
+
+    def trace_all(self, rays_dev, n, counts_dev, sums_dev, flags=0, stream=None):
+        self._check(self.lib.prt_trace_all(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(counts_dev),
+                                           _dev_ptr(sums_dev), int(flags), _stream_ptr(stream)))
+
+    def trace_closest_host(self, rays, flags=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        self._check(self.lib.prt_trace_closest_host(self.h, _np_ptr(rays), rays.shape[0], _np_ptr(hits),
+                                                    int(flags)))
+        return hits
+
+    # -- render ---------------------------------------------------------------
+    @staticmethod
+    def render_params(seed=1, spp_begin=0, spp_end=1, max_depth=5, rr_start=0xFFFFFFFF,
+                      light_color=(0.9, 0.85, 0.7), tmin=1e-5, tmax=99999.9):
+        p = PrtRenderParams()
+        p.seed, p.spp_begin, p.spp_end = int(seed), int(spp_begin), int(spp_end)
+        p.max_depth, p.rr_start = int(max_depth), int(rr_start)
+        for k in range(3):
+            p.light_color[k] = float(light_color[k])
+        p.tmin, p.tmax, p.flags = float(tmin), float(tmax), 0
+        return p
+
+    def render(self, params, accum_dev, prim_ids_dev=None, stream=None):
+        self._check(self.lib.prt_render(self.h, C.byref(params), _dev_ptr(accum_dev),
+                                        _dev_ptr(prim_ids_dev), _stream_ptr(stream)))
+
+    def render_host(self, params, accum):
+        assert accum.dtype == np.float32 and accum.flags.c_contiguous
+        self._check(self.lib.prt_render_host(self.h, C.byref(params), _np_ptr(accum)))
+
+    def set_wave_paths(self, paths):
+        self._check(self.lib.prt_set_wave_paths(self.h, int(paths)))
+
+    def counters(self):
+        c = PrtCounters()
+        self._check(self.lib.prt_get_counters(self.h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in PrtCounters._fields_}
+
+    def reset_counters(self):
+        self._check(self.lib.prt_reset_counters(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.prt_synchronize(self.h))

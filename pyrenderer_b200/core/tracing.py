@@ -1,0 +1,103 @@
+"""Render entry points (reference: core/tracing.py:47-155 PathTracer.trace, and
+the pixel x sample loops of main.py:28-59 / main_taichi.py:80-99).
+
+``render`` replaces the whole loop with ONE C-ABI call per frame: the wavefront
+integrator (csrc/wavefront.cu) adds samples [spp_begin, spp_end) of every
+pixel to an fp32 accumulation buffer owned by a torch tensor.
+``render_distributed`` shards the sample range over the ranks of the default
+torch.distributed group (replicated scene + BVH) and sums the buffers with one
+all-reduce (NCCL over NVLink on GPUs).
+"""
+import numpy as np
+
+from ..mathematics.constants import LIGHT_COLOR, T_MAX, T_MIN
+
+RR_OFF = 0xFFFFFFFF
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def new_accum(camera, device=0):
+    torch = _torch()
+    w, h = camera.get_resolution()
+    return torch.zeros((h, w, 4), dtype=torch.float32, device=f"cuda:{device}")
+
+
+def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_OFF, device=0,
+           accum=None, want_prim_ids=False, light_color=LIGHT_COLOR, stream=None):
+    """Add samples [spp_begin, spp_begin+spp) to ``accum`` (created if None).
+
+    Returns ``accum`` (torch f32 [h, w, 4]: rgb sums + sample count, row 0 = bottom
+    image row), or ``(accum, prim_ids)`` with ``want_prim_ids``.
+    """
+    torch = _torch()
+    ctx = scene.commit(device)
+    ctx.set_camera(*camera.device_record())
+    if accum is None:
+        accum = new_accum(camera, device)
+    w, h = camera.get_resolution()
+    ids = None
+    if want_prim_ids:
+        ids = torch.full((h, w, spp), -2, dtype=torch.int32, device=accum.device)
+    params = ctx.render_params(seed=seed, spp_begin=spp_begin, spp_end=spp_begin + spp,
+                               max_depth=max_depth, rr_start=rr_start, light_color=light_color,
+                               tmin=T_MIN, tmax=T_MAX)
+    ctx.render(params, accum, ids, stream)
+    return (accum, ids) if want_prim_ids else accum
+
+
+def shard_samples(spp, rank, world):
+    """Contiguous sample range of ``rank``: [r*S/G, (r+1)*S/G)."""
+    return (spp * rank) // world, (spp * (rank + 1)) // world
+
+
+def render_distributed(scene, camera, spp, max_depth=5, seed=1, rr_start=RR_OFF, device=0,
+                       accum=None, group=None):
+    """Every rank renders its sample shard; one all-reduce sums the buffers."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    s0, s1 = shard_samples(spp, rank, world)
+    accum = render(scene, camera, spp=s1 - s0, max_depth=max_depth, seed=seed, spp_begin=s0,
+                   rr_start=rr_start, device=device, accum=accum)
+    if world > 1:
+        dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
+    return accum
+
+
+def resolve(accum):
+    """accum [h,w,4] -> mean radiance [h,w,3] (main.py:37 ``total/SAMPLES``)."""
+    a = accum.detach().cpu().numpy() if hasattr(accum, "detach") else np.asarray(accum)
+    n = np.maximum(a[..., 3:4], 1.0)
+    return a[..., :3] / n
+
+
+def to_image(accum, tonemap=None):
+    """Mean radiance as the reference stores it: ``image[W-1-j, i]`` (main.py:55),
+    i.e. top row first.  tonemap: None (main.py), "sqrt" (main_taichi.py:61-64)."""
+    img = resolve(accum)[::-1]
+    if tonemap == "sqrt":
+        img = np.sqrt(np.maximum(img, 0.0))
+    return np.ascontiguousarray(img)
+
+
+def to_uint8(img):
+    """``image*255 -> uint8`` of main.py:57-58, with a clamp instead of wrap-around."""
+    return (np.clip(img, 0.0, 1.0) * 255.0).astype(np.uint8)
+
+
+class PathTracer:
+    """Shape of the reference class (core/tracing.py:47-50): bound to a scene, a
+    depth and an image size; ``trace_image`` is the batched form of ``trace``."""
+
+    def __init__(self, world, depth, img_w=None, img_h=None):
+        self.world = world
+        self.depth = depth
+        self.img_w, self.img_h = img_w, img_h
+
+    def trace_image(self, camera, spp=1, seed=1, spp_begin=0, accum=None, device=0):
+        return render(self.world, camera, spp=spp, max_depth=self.depth, seed=seed,
+                      spp_begin=spp_begin, accum=accum, device=device)

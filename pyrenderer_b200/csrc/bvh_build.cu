@@ -1,0 +1,496 @@
+// bvh_build.cu -- GPU LBVH build emitting the 32-byte quantised node layout.
+//
+// Pipeline (all on the device, no host round trips except the final sizes):
+//   1. bounds_kernel     scene AABB (block reduce + ordered-int atomics)
+//   2. morton_kernel     30-bit Morton code of each triangle's box centre
+//   3. radix sort        (key, triangle) pairs, cub::DeviceRadixSort
+//   4. hierarchy_kernel  Karras 2012 "Maximizing parallelism in the construction
+//                        of BVHs, octrees and k-d trees": one thread per internal node
+//   5. refit_kernel      bottom-up with arrival flags: boxes, SAH cost, SAH tree
+//                        rotations (3-leaf treelets) and SAH leaf collapse (<= 7 tris)
+//   6. emit_kernel       DFS pre-order record index + DFS triangle offset per surviving
+//                        node (walk to the root), conservative 8-bit quantisation,
+//                        triangles rewritten in leaf order
+//
+// Replaces: BVH.build / build_helper / sah_heuristic accelerators/bvh.py:70-215
+// (recursive binned SAH on the CPU), Aggregator.update accelerators/aggregator.py:25-55
+// (flat soup for zero-thickness primitives: no special path here, flat boxes
+// quantise fine) and BVH.build accelerators/bvh_taichi.py:126-161.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "context.cuh"
+#include "bvh.cuh"
+
+namespace prt {
+
+namespace {
+
+struct BuildBuffers {
+    uint32_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int* left = nullptr;     // [N-1]
+    int* right = nullptr;    // [N-1]
+    int* parent = nullptr;   // [2N-1]
+    float4* bmin = nullptr;  // [2N-1]  w = SAH cost of the subtree
+    float4* bmax = nullptr;  // [2N-1]
+    uint32_t* tcount = nullptr;  // [2N-1] triangles below
+    uint32_t* icount = nullptr;  // [2N-1] surviving records below (incl. self)
+    uint8_t* collapsed = nullptr;  // [2N-1]
+    unsigned int* flags = nullptr;  // [N-1]
+    int* scene_box = nullptr;       // 6 ordered ints
+    unsigned int* max_depth = nullptr;
+    void free_all() {
+        cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
+        cudaFree(cub_tmp); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(bmin);
+        cudaFree(bmax); cudaFree(tcount); cudaFree(icount); cudaFree(collapsed); cudaFree(flags);
+        cudaFree(scene_box); cudaFree(max_depth);
+    }
+};
+
+__device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ void tri_box(const float4* v, uint32_t t, float3& lo, float3& hi) {
+    float4 a = v[3ull * t], b = v[3ull * t + 1], c = v[3ull * t + 2];
+    lo = make_float3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+    hi = make_float3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+}
+
+__global__ void init_box_kernel(int* box) {
+    if (threadIdx.x < 3) box[threadIdx.x] = f2ord(3.4e38f);
+    else if (threadIdx.x < 6) box[threadIdx.x] = f2ord(-3.4e38f);
+}
+
+__global__ void bounds_kernel(const float4* __restrict__ v, uint32_t nt, int* box) {
+    float3 lo = make_float3(3.4e38f, 3.4e38f, 3.4e38f), hi = make_float3(-3.4e38f, -3.4e38f, -3.4e38f);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+        float3 a, b;
+        tri_box(v, t, a, b);
+        lo = make_float3(fminf(lo.x, a.x), fminf(lo.y, a.y), fminf(lo.z, a.z));
+        hi = make_float3(fmaxf(hi.x, b.x), fmaxf(hi.y, b.y), fmaxf(hi.z, b.z));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(~0u, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(~0u, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(~0u, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(~0u, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(~0u, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(~0u, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(box + 0, f2ord(lo.x)); atomicMin(box + 1, f2ord(lo.y)); atomicMin(box + 2, f2ord(lo.z));
+        atomicMax(box + 3, f2ord(hi.x)); atomicMax(box + 4, f2ord(hi.y)); atomicMax(box + 5, f2ord(hi.z));
+    }
+}
+
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void morton_kernel(const float4* __restrict__ v, uint32_t nt, const int* __restrict__ box,
+                              uint32_t* keys, uint32_t* vals) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    float3 smin = make_float3(ord2f(box[0]), ord2f(box[1]), ord2f(box[2]));
+    float3 smax = make_float3(ord2f(box[3]), ord2f(box[4]), ord2f(box[5]));
+    float3 lo, hi;
+    tri_box(v, t, lo, hi);
+    float ex = smax.x - smin.x, ey = smax.y - smin.y, ez = smax.z - smin.z;
+    float cx = ex > 0.f ? (0.5f * (lo.x + hi.x) - smin.x) / ex : 0.f;
+    float cy = ey > 0.f ? (0.5f * (lo.y + hi.y) - smin.y) / ey : 0.f;
+    float cz = ez > 0.f ? (0.5f * (lo.z + hi.z) - smin.z) / ez : 0.f;
+    uint32_t x = (uint32_t)fminf(fmaxf(cx * 1024.f, 0.f), 1023.f);
+    uint32_t y = (uint32_t)fminf(fmaxf(cy * 1024.f, 0.f), 1023.f);
+    uint32_t z = (uint32_t)fminf(fmaxf(cz * 1024.f, 0.f), 1023.f);
+    keys[t] = (expand10(x) << 2) | (expand10(y) << 1) | expand10(z);
+    vals[t] = t;
+}
+
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+
+// node ids: internal i -> i (0..n-2), leaf j -> (n-1)+j
+__global__ void hierarchy_kernel(const uint32_t* __restrict__ keys, int n, int* left, int* right,
+                                 int* parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lc = (min(i, j) == gamma) ? (n - 1) + gamma : gamma;
+    int rc = (max(i, j) == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
+    left[i] = lc;
+    right[i] = rc;
+    parent[lc] = i;
+    parent[rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__device__ __forceinline__ float box_area(float3 lo, float3 hi) {
+    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return 2.0f * (ex * ey + ey * ez + ez * ex);
+}
+__device__ __forceinline__ float union_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+    float3 lo = make_float3(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z));
+    float3 hi = make_float3(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z));
+    return box_area(lo, hi);
+}
+
+struct RefitParams {
+    int n;
+    uint32_t max_leaf;
+    float cn, ct;
+    int rotations;
+};
+
+// Everything refit_kernel reads may have been written by another SM earlier in
+// the same launch (ordered by the arrival flags), so all loads bypass L1 (.cg).
+__device__ __forceinline__ void update_node(int x, const int* left, const int* right, float4* bmin,
+                                            float4* bmax, uint32_t* tcount, uint32_t* icount,
+                                            uint8_t* collapsed, const RefitParams& P) {
+    int l = __ldcg(left + x), r = __ldcg(right + x);
+    float4 llo = __ldcg(bmin + l), lhi = __ldcg(bmax + l), rlo = __ldcg(bmin + r), rhi = __ldcg(bmax + r);
+    float3 lo = make_float3(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z));
+    float3 hi = make_float3(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z));
+    float sa = box_area(lo, hi);
+    uint32_t tc = __ldcg(tcount + l) + __ldcg(tcount + r);
+    float c_int = P.cn * sa + llo.w + rlo.w;
+    float c_leaf = P.ct * (float)tc * sa;
+    bool col = (x != 0) && tc <= P.max_leaf && c_leaf <= c_int;
+    __stcg(bmin + x, make_float4(lo.x, lo.y, lo.z, col ? c_leaf : c_int));
+    __stcg(bmax + x, make_float4(hi.x, hi.y, hi.z, sa));
+    __stcg(tcount + x, tc);
+    __stcg(icount + x, col ? 0u : 1u + __ldcg(icount + l) + __ldcg(icount + r));
+    __stcg(collapsed + x, (uint8_t)(col ? 1 : 0));
+}
+
+__global__ void refit_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vals,
+                             int* left, int* right, int* parent, float4* bmin, float4* bmax,
+                             uint32_t* tcount, uint32_t* icount, uint8_t* collapsed,
+                             unsigned int* flags, RefitParams P) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    int n = P.n;
+    int node = (n - 1) + j;
+    {
+        float3 lo, hi;
+        tri_box(verts, vals[j], lo, hi);
+        float sa = box_area(lo, hi);
+        __stcg(bmin + node, make_float4(lo.x, lo.y, lo.z, P.ct * sa));
+        __stcg(bmax + node, make_float4(hi.x, hi.y, hi.z, sa));
+        __stcg(tcount + node, 1u);
+        __stcg(icount + node, 0u);
+    }
+    if (n == 1) return;
+    int p = __ldcg(parent + node);
+    while (true) {
+        __threadfence();
+        unsigned int old = atomicAdd(flags + p, 1u);
+        if (old == 0) return;  // the sibling subtree is not finished; its thread continues
+        __threadfence();
+        // this thread now owns the whole subtree of p
+        if (P.rotations) {
+            int l = __ldcg(left + p), r = __ldcg(right + p);
+            float4 llo = __ldcg(bmin + l), lhi = __ldcg(bmax + l), rlo = __ldcg(bmin + r), rhi = __ldcg(bmax + r);
+            float best = 0.0f;
+            int which = -1;
+            bool r_int = r < n - 1 && !__ldcg(collapsed + r);
+            bool l_int = l < n - 1 && !__ldcg(collapsed + l);
+            int rl = -1, rr = -1, ll = -1, lr = -1;
+            if (r_int) {
+                rl = __ldcg(left + r); rr = __ldcg(right + r);
+                float g0 = rhi.w - union_area(llo, lhi, __ldcg(bmin + rr), __ldcg(bmax + rr));  // swap l <-> rl
+                float g1 = rhi.w - union_area(llo, lhi, __ldcg(bmin + rl), __ldcg(bmax + rl));  // swap l <-> rr
+                if (g0 > best) { best = g0; which = 0; }
+                if (g1 > best) { best = g1; which = 1; }
+            }
+            if (l_int) {
+                ll = __ldcg(left + l); lr = __ldcg(right + l);
+                float g2 = lhi.w - union_area(rlo, rhi, __ldcg(bmin + lr), __ldcg(bmax + lr));  // swap r <-> ll
+                float g3 = lhi.w - union_area(rlo, rhi, __ldcg(bmin + ll), __ldcg(bmax + ll));  // swap r <-> lr
+                if (g2 > best) { best = g2; which = 2; }
+                if (g3 > best) { best = g3; which = 3; }
+            }
+            if (which == 0) { __stcg(left + r, l); __stcg(left + p, rl); __stcg(parent + l, r); __stcg(parent + rl, p); }
+            else if (which == 1) { __stcg(right + r, l); __stcg(left + p, rr); __stcg(parent + l, r); __stcg(parent + rr, p); }
+            else if (which == 2) { __stcg(left + l, r); __stcg(right + p, ll); __stcg(parent + r, l); __stcg(parent + ll, p); }
+            else if (which == 3) { __stcg(right + l, r); __stcg(right + p, lr); __stcg(parent + r, l); __stcg(parent + lr, p); }
+            if (which == 0 || which == 1) update_node(r, left, right, bmin, bmax, tcount, icount, collapsed, P);
+            if (which == 2 || which == 3) update_node(l, left, right, bmin, bmax, tcount, icount, collapsed, P);
+        }
+        update_node(p, left, right, bmin, bmax, tcount, icount, collapsed, P);
+        if (p == 0) return;
+        p = __ldcg(parent + p);
+    }
+}
+
+__device__ __forceinline__ uint32_t quant_axis_exp(float extent) {
+    if (!(extent > 0.0f)) return 1u;
+    int k;
+    frexpf(extent * (1.0f / 254.0f), &k);  // extent/254 = m * 2^k, m in [0.5,1)  =>  2^k >= extent/254
+    int e = k + 127;
+    return (uint32_t)min(max(e, 1), 254);
+}
+
+__device__ __forceinline__ bool quant_planes(float o, float scale, float lo, float hi, uint32_t& qlo,
+                                             uint32_t& qhi) {
+    float inv = 1.0f / scale;  // exact: power of two
+    int a = (int)floorf((lo - o) * inv), b = (int)ceilf((hi - o) * inv);
+    a = min(max(a, 0), 255);
+    b = min(max(b, 0), 255);
+    while (a > 0 && fmaf((float)a, scale, o) > lo) --a;
+    while (b < 255 && fmaf((float)b, scale, o) < hi) ++b;
+    qlo = (uint32_t)a;
+    qhi = (uint32_t)b;
+    return fmaf((float)a, scale, o) <= lo && fmaf((float)b, scale, o) >= hi;
+}
+
+__device__ __forceinline__ void write_leaf_tris(const float4* __restrict__ verts,
+                                                const uint32_t* __restrict__ vals, const int* left,
+                                                const int* right, int n, int x, uint32_t start,
+                                                float4* out) {
+    int stack[16];
+    int sp = 0;
+    uint32_t k = start;
+    int cur = x;
+    while (true) {
+        if (cur >= n - 1) {
+            uint32_t t = vals[cur - (n - 1)];
+            out[3ull * k] = verts[3ull * t];
+            out[3ull * k + 1] = verts[3ull * t + 1];
+            out[3ull * k + 2] = verts[3ull * t + 2];
+            ++k;
+            if (sp == 0) break;
+            cur = stack[--sp];
+        } else {
+            if (sp < 16) stack[sp++] = right[cur];
+            cur = left[cur];
+        }
+    }
+}
+
+__global__ void emit_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vals,
+                            const int* __restrict__ left, const int* __restrict__ right,
+                            const int* __restrict__ parent, const float4* __restrict__ bmin,
+                            const float4* __restrict__ bmax, const uint32_t* __restrict__ tcount,
+                            const uint32_t* __restrict__ icount, const uint8_t* __restrict__ collapsed,
+                            int n, Node32* nodes, float4* tris_out, unsigned int* max_depth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (collapsed[i]) return;
+    uint32_t idx = 0, tstart = 0, depth = 0;
+    for (int c = i; c != 0;) {
+        int p = parent[c];
+        if (collapsed[p]) return;
+        int lp = left[p];
+        if (c != lp) { idx += 1 + icount[lp]; tstart += tcount[lp]; }
+        else idx += 1;
+        c = p;
+        ++depth;
+    }
+    atomicMax(max_depth, depth + 1);
+    int l = left[i], r = right[i];
+    bool lleaf = l >= n - 1 || collapsed[l], rleaf = r >= n - 1 || collapsed[r];
+    uint32_t c0 = lleaf ? tcount[l] : 0u, c1 = rleaf ? tcount[r] : 0u;
+    float4 lo4 = bmin[i], hi4 = bmax[i];
+    float4 llo = bmin[l], lhi = bmax[l], rlo = bmin[r], rhi = bmax[r];
+    float o[3] = {lo4.x, lo4.y, lo4.z};
+    float ext[3] = {hi4.x - lo4.x, hi4.y - lo4.y, hi4.z - lo4.z};
+    float clo[2][3] = {{llo.x, llo.y, llo.z}, {rlo.x, rlo.y, rlo.z}};
+    float chi[2][3] = {{lhi.x, lhi.y, lhi.z}, {rhi.x, rhi.y, rhi.z}};
+    uint32_t e[3], q[2][2][3];
+    for (int a = 0; a < 3; ++a) {
+        e[a] = quant_axis_exp(ext[a]);
+        while (true) {
+            float scale = __uint_as_float(e[a] << 23);
+            bool ok = quant_planes(o[a], scale, clo[0][a], chi[0][a], q[0][0][a], q[0][1][a]);
+            ok = quant_planes(o[a], scale, clo[1][a], chi[1][a], q[1][0][a], q[1][1][a]) && ok;
+            if (ok || e[a] >= 254) break;
+            ++e[a];
+        }
+    }
+    Node32 nd;
+    nd.ox = o[0]; nd.oy = o[1]; nd.oz = o[2];
+    nd.em = e[0] | (e[1] << 8) | (e[2] << 16) | (c0 << 24) | (c1 << 28);
+    nd.q0 = q[0][0][0] | (q[0][0][1] << 8) | (q[0][0][2] << 16) | (q[0][1][0] << 24);
+    nd.q1 = q[0][1][1] | (q[0][1][2] << 8) | (q[1][0][0] << 16) | (q[1][0][1] << 24);
+    nd.q2 = q[1][0][2] | (q[1][1][0] << 8) | (q[1][1][1] << 16) | (q[1][1][2] << 24);
+    if (!lleaf && !rleaf) nd.link = idx + 1 + icount[l];
+    else if (lleaf) nd.link = tstart;
+    else nd.link = tstart + tcount[l];
+    nodes[idx] = nd;
+    if (lleaf) write_leaf_tris(verts, vals, left, right, n, l, tstart, tris_out);
+    if (rleaf) write_leaf_tris(verts, vals, left, right, n, r, tstart + tcount[l], tris_out);
+}
+
+// n == 1: a single record whose child0 is the only triangle and child1 is absent
+__global__ void emit_single_kernel(const float4* __restrict__ verts, Node32* nodes, float4* tris_out) {
+    float3 lo, hi;
+    tri_box(verts, 0, lo, hi);
+    float o[3] = {lo.x, lo.y, lo.z}, l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+    uint32_t e[3], ql[3], qh[3];
+    for (int a = 0; a < 3; ++a) {
+        e[a] = quant_axis_exp(h3[a] - l3[a]);
+        while (!quant_planes(o[a], __uint_as_float(e[a] << 23), l3[a], h3[a], ql[a], qh[a]) && e[a] < 254) ++e[a];
+    }
+    Node32 nd;
+    nd.ox = o[0]; nd.oy = o[1]; nd.oz = o[2];
+    nd.em = e[0] | (e[1] << 8) | (e[2] << 16) | (1u << 24) | (0xFu << 28);
+    nd.q0 = ql[0] | (ql[1] << 8) | (ql[2] << 16) | (qh[0] << 24);
+    nd.q1 = qh[1] | (qh[2] << 8);
+    nd.q2 = 0;
+    nd.link = 0;
+    nodes[0] = nd;
+    tris_out[0] = verts[0]; tris_out[1] = verts[1]; tris_out[2] = verts[2];
+}
+
+}  // namespace
+
+#define BUILD_TRY(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ctx->set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            B.free_all();                                                                    \
+            return PRT_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* stats, bool* too_deep) {
+    BuildBuffers B;
+    const uint32_t nt = ctx->nt;
+    const int n = (int)nt;
+    *too_deep = false;
+    cudaFree(ctx->nodes); ctx->nodes = nullptr;
+    cudaFree(ctx->tris_leaf); ctx->tris_leaf = nullptr;
+    ctx->n_nodes = 0;
+    ctx->bvh_built = false;
+    prt_bvh_stats st = {};
+    st.n_tris = nt;
+    st.max_leaf_tris = opt.max_leaf_tris;
+    if (nt == 0) {
+        ctx->bvh_built = true;
+        ctx->bvh_stats = st;
+        if (stats) *stats = st;
+        return PRT_OK;
+    }
+    cudaEvent_t ev[7];
+    for (auto& e : ev) cudaEventCreate(&e);
+    const size_t nn = 2 * (size_t)nt - 1;
+    BUILD_TRY(cudaMalloc(&ctx->tris_leaf, sizeof(float4) * 3 * (size_t)nt));
+    BUILD_TRY(cudaMalloc(&B.scene_box, 6 * sizeof(int)));
+    BUILD_TRY(cudaMalloc(&B.max_depth, sizeof(unsigned int)));
+    BUILD_TRY(cudaMemset(B.max_depth, 0, sizeof(unsigned int)));
+    for (int k = 0; k < 2; ++k) {
+        BUILD_TRY(cudaMalloc(&B.keys[k], sizeof(uint32_t) * nt));
+        BUILD_TRY(cudaMalloc(&B.vals[k], sizeof(uint32_t) * nt));
+    }
+    BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, B.cub_bytes, B.keys[0], B.keys[1], B.vals[0], B.vals[1], n, 0, 30));
+    BUILD_TRY(cudaMalloc(&B.cub_tmp, B.cub_bytes ? B.cub_bytes : 16));
+    BUILD_TRY(cudaMalloc(&B.left, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
+    BUILD_TRY(cudaMalloc(&B.right, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
+    BUILD_TRY(cudaMalloc(&B.parent, sizeof(int) * nn));
+    BUILD_TRY(cudaMalloc(&B.bmin, sizeof(float4) * nn));
+    BUILD_TRY(cudaMalloc(&B.bmax, sizeof(float4) * nn));
+    BUILD_TRY(cudaMalloc(&B.tcount, sizeof(uint32_t) * nn));
+    BUILD_TRY(cudaMalloc(&B.icount, sizeof(uint32_t) * nn));
+    BUILD_TRY(cudaMalloc(&B.collapsed, nn));
+    BUILD_TRY(cudaMalloc(&B.flags, sizeof(unsigned int) * (nt > 1 ? nt - 1 : 1)));
+    BUILD_TRY(cudaMemset(B.flags, 0, sizeof(unsigned int) * (nt > 1 ? nt - 1 : 1)));
+    BUILD_TRY(cudaMemset(B.collapsed, 0, nn));
+
+    const int T = 256;
+    const unsigned gN = (nt + T - 1) / T;
+    cudaEventRecord(ev[0]);
+    init_box_kernel<<<1, 32>>>(B.scene_box);
+    bounds_kernel<<<min(gN, (unsigned)ctx->num_sms * 8u), T>>>(ctx->verts_gid, nt, B.scene_box);
+    morton_kernel<<<gN, T>>>(ctx->verts_gid, nt, B.scene_box, B.keys[0], B.vals[0]);
+    cudaEventRecord(ev[1]);
+    BUILD_TRY(cub::DeviceRadixSort::SortPairs(B.cub_tmp, B.cub_bytes, B.keys[0], B.keys[1], B.vals[0], B.vals[1], n, 0, 30));
+    cudaEventRecord(ev[2]);
+    if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[1], n, B.left, B.right, B.parent);
+    cudaEventRecord(ev[3]);
+    RefitParams P;
+    P.n = n; P.max_leaf = opt.max_leaf_tris; P.cn = opt.cost_node; P.ct = opt.cost_tri;
+    P.rotations = (int)opt.rotations;
+    refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[1], B.left, B.right, B.parent, B.bmin, B.bmax,
+                            B.tcount, B.icount, B.collapsed, B.flags, P);
+    cudaEventRecord(ev[4]);
+    BUILD_TRY(cudaGetLastError());
+    uint32_t n_rec = 1;
+    float4 root_lo = {}, root_hi = {};
+    if (n > 1) {
+        BUILD_TRY(cudaMemcpy(&n_rec, B.icount, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        BUILD_TRY(cudaMemcpy(&root_lo, B.bmin, sizeof(float4), cudaMemcpyDeviceToHost));
+        BUILD_TRY(cudaMemcpy(&root_hi, B.bmax, sizeof(float4), cudaMemcpyDeviceToHost));
+    }
+    BUILD_TRY(cudaMalloc(&ctx->nodes, sizeof(Node32) * (size_t)n_rec));
+    cudaEventRecord(ev[5]);
+    if (n > 1)
+        emit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[1], B.left, B.right, B.parent, B.bmin, B.bmax,
+                               B.tcount, B.icount, B.collapsed, n, ctx->nodes, ctx->tris_leaf, B.max_depth);
+    else
+        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tris_leaf);
+    cudaEventRecord(ev[6]);
+    BUILD_TRY(cudaDeviceSynchronize());
+    unsigned int depth = 0;
+    BUILD_TRY(cudaMemcpy(&depth, B.max_depth, sizeof depth, cudaMemcpyDeviceToHost));
+    float ms[6];
+    for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    st.n_nodes = n_rec;
+    st.sah_cost = (n > 1 && root_hi.w > 0.f) ? root_lo.w / root_hi.w : 0.f;
+    st.ms_morton = ms[0]; st.ms_sort = ms[1]; st.ms_hierarchy = ms[2]; st.ms_refit = ms[3];
+    st.ms_emit = ms[5];
+    st.ms_total = ms[0] + ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
+    st.depth = depth;
+    B.free_all();
+    if (depth + 2 >= (unsigned)kMaxStack) { *too_deep = true; return PRT_OK; }
+    ctx->n_nodes = n_rec;
+    ctx->bvh_built = true;
+    ctx->bvh_stats = st;
+    if (stats) *stats = st;
+    return PRT_OK;
+}
+
+int build_bvh(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats) {
+    prt_bvh_options o;
+    o.max_leaf_tris = 4; o.cost_node = 1.0f; o.cost_tri = 1.0f; o.rotations = 1;
+    if (opts) o = *opts;
+    if (o.max_leaf_tris < 1 || o.max_leaf_tris > 7) { ctx->set_error("bvh: max_leaf_tris must be in 1..7"); return PRT_ERR_INVALID; }
+    if (!ctx->scene_set) { ctx->set_error("bvh: no scene"); return PRT_ERR_STATE; }
+    bool too_deep = false;
+    int rc = build_once(ctx, o, stats, &too_deep);
+    if (rc != PRT_OK) return rc;
+    if (too_deep) {  // rotations can deepen a degenerate tree; the Karras tree is bounded (<= 62)
+        o.rotations = 0;
+        rc = build_once(ctx, o, stats, &too_deep);
+        if (rc != PRT_OK) return rc;
+        if (too_deep) { ctx->set_error("bvh: tree deeper than the traversal stack"); return PRT_ERR_STATE; }
+    }
+    return PRT_OK;
+}
+
+}  // namespace prt

@@ -1,0 +1,70 @@
+// common.cuh -- shared types of the sm_100a path-tracing core.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/prt.h"
+
+namespace prt {
+
+constexpr int kSmemStack = 24;          // per-thread traversal stack entries held in shared memory
+constexpr int kTraceThreads = 128;      // CTA size of the traversal kernels
+constexpr uint32_t kLeafFlag = 0x80000000u;
+
+// ---- device scene ---------------------------------------------------------
+// Triangles live in HBM as 3 x float4 (48 B), in BVH leaf (DFS) order so that a
+// leaf's triangles are contiguous:  (p0.xyz, bits(global id)), (p1.xyz,
+// bits(material)), (p2.xyz, 0).  Shading data (normal + material) is a separate
+// float4 array indexed by the GLOBAL id, touched once per path vertex only.
+struct Node32 {        // 32 B, two float4 / one sector
+    float ox, oy, oz;  // frame origin
+    uint32_t em;       // ex | ey<<8 | ez<<16 | meta<<24   (scale = 2^(e-127)); meta: cnt0 | cnt1<<4
+    uint32_t q0;       // child0: lo.x lo.y lo.z hi.x
+    uint32_t q1;       // child0: hi.y hi.z | child1: lo.x lo.y
+    uint32_t q2;       // child1: lo.z hi.x hi.y hi.z
+    uint32_t link;     // see bvh.cuh
+};
+static_assert(sizeof(Node32) == 32, "node must be 32 bytes");
+
+struct SceneDev {
+    const float4* tris;      // [nt*3] leaf order
+    const Node32* nodes;     // [n_nodes]
+    const float4* shade;     // [nt] by global id: normal.xyz, bits(material)
+    const prt_material* mats;
+    const uint32_t* light_tris;  // global ids
+    const float4* verts_gid;     // [nt*3] by global id (light sampling)
+    uint32_t nt, n_nodes, nl, nm;
+};
+
+struct Counters {
+    unsigned long long rays_closest, rays_shadow, node_visits, tri_tests, flagged_rays, paths;
+};
+
+// ---- small vector helpers ---------------------------------------------------
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return make_float3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize(float3 a) {
+    float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+    return make_float3(a.x / n, a.y / n, a.z / n);
+}
+__device__ __forceinline__ float3 xyz(float4 a) { return make_float3(a.x, a.y, a.z); }
+
+}  // namespace prt
+
+#define PRT_CUDA_TRY(ctx, expr)                                                          \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            (ctx)->set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,                \
+                             cudaGetErrorString(_e));                                    \
+            return PRT_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)

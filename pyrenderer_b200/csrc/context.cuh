@@ -1,0 +1,75 @@
+// context.cuh -- the library-owned state behind prt_ctx.
+#pragma once
+#include <stdarg.h>
+
+#include <string>
+
+#include "common.cuh"
+
+struct prt_ctx {
+    int device = 0;
+    int num_sms = 148;
+    char err[512] = {0};
+
+    // scene (device)
+    uint32_t nt = 0, nm = 0, nl = 0;
+    float4* verts_gid = nullptr;   // [nt*3] triangles by global id (w unused)
+    float4* shade = nullptr;       // [nt] normal.xyz, bits(material)
+    prt_material* mats = nullptr;  // [nm]
+    uint32_t* light_tris = nullptr;
+    bool scene_set = false;
+
+    // BVH (device)
+    float4* tris_leaf = nullptr;   // [nt*3] leaf order, w carries gid / material
+    prt::Node32* nodes = nullptr;
+    uint32_t n_nodes = 0;
+    bool bvh_built = false;
+    prt_bvh_stats bvh_stats = {};
+
+    // camera
+    prt_camera cam = {};
+    bool cam_set = false;
+
+    // counters + exact-mode scratch
+    prt::Counters* counters = nullptr;  // device
+    uint32_t* flag_list = nullptr;
+    unsigned int* flag_count = nullptr;
+    uint64_t flag_cap = 0;
+
+    // wavefront state (wavefront.cu)
+    void* wf = nullptr;
+    uint64_t wave_paths = 4ull << 20;
+
+    void set_error(const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, sizeof err, fmt, ap);
+        va_end(ap);
+    }
+
+    prt::SceneDev scene_dev() const {
+        prt::SceneDev s;
+        s.tris = bvh_built ? tris_leaf : nullptr;
+        s.nodes = nodes;
+        s.shade = shade;
+        s.mats = mats;
+        s.light_tris = light_tris;
+        s.verts_gid = verts_gid;
+        s.nt = nt; s.n_nodes = n_nodes; s.nl = nl; s.nm = nm;
+        return s;
+    }
+};
+
+namespace prt {
+// traverse.cu
+int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* out0, void* out1,
+                 uint32_t flags, cudaStream_t stream);
+// bvh_build.cu
+int build_bvh(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats);
+// wavefront.cu
+int generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int jitter, float tmin,
+                  float tmax, float4* rays, cudaStream_t stream);
+int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim_ids,
+           cudaStream_t stream);
+void wavefront_free(prt_ctx* ctx);
+}  // namespace prt

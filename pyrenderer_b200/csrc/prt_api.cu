@@ -1,0 +1,313 @@
+// prt_api.cu -- extern "C" entry points declared in include/prt.h.
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "context.cuh"
+
+static char g_create_error[512] = "";
+
+namespace prt {
+
+// pack host triangles into the device layout: 3 x float4 per triangle with
+// w = bits(global id), bits(material), 0
+__global__ void pack_tris_kernel(const float* __restrict__ v, const uint32_t* __restrict__ tri_mat,
+                                 uint32_t nt, float4* out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const float* p = v + 9ull * t;
+    uint32_t m = tri_mat ? tri_mat[t] : 0u;
+    out[3ull * t] = make_float4(p[0], p[1], p[2], __uint_as_float(t));
+    out[3ull * t + 1] = make_float4(p[3], p[4], p[5], __uint_as_float(m));
+    out[3ull * t + 2] = make_float4(p[6], p[7], p[8], 0.0f);
+}
+
+__global__ void pack_shade_kernel(const float* __restrict__ v, const float* __restrict__ normals,
+                                  const uint32_t* __restrict__ tri_mat, uint32_t nt, float4* shade) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    float3 n;
+    if (normals) {
+        n = make_float3(normals[3ull * t], normals[3ull * t + 1], normals[3ull * t + 2]);
+    } else {
+        const float* p = v + 9ull * t;
+        float3 e1 = make_float3(p[3] - p[0], p[4] - p[1], p[5] - p[2]);
+        float3 e2 = make_float3(p[6] - p[0], p[7] - p[1], p[8] - p[2]);
+        n = normalize(cross(e1, e2));
+    }
+    shade[t] = make_float4(n.x, n.y, n.z, __uint_as_float(tri_mat ? tri_mat[t] : 0u));
+}
+
+static void free_scene(prt_ctx* c) {
+    cudaFree(c->verts_gid); cudaFree(c->shade); cudaFree(c->mats); cudaFree(c->light_tris);
+    cudaFree(c->tris_leaf); cudaFree(c->nodes);
+    c->verts_gid = nullptr; c->shade = nullptr; c->mats = nullptr; c->light_tris = nullptr;
+    c->tris_leaf = nullptr; c->nodes = nullptr;
+    c->nt = c->nm = c->nl = c->n_nodes = 0;
+    c->scene_set = false; c->bvh_built = false;
+}
+
+static int set_scene_common(prt_ctx* ctx, const float* verts_dev, const float* normals_dev,
+                            const uint32_t* tri_mat_dev, uint32_t nt, const prt_material* mats_host,
+                            uint32_t nm, const uint32_t* light_host, uint32_t nl, cudaStream_t s) {
+    free_scene(ctx);
+    prt_material def;
+    memset(&def, 0, sizeof def);
+    def.albedo[0] = def.albedo[1] = def.albedo[2] = 0.5f;
+    def.type = PRT_MAT_LAMBERT; def.ior = 1.0f; def.two_sided = 1;
+    if (!mats_host || nm == 0) { mats_host = &def; nm = 1; }
+    size_t ntz = nt ? nt : 1;
+    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->verts_gid, sizeof(float4) * 3 * ntz));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->shade, sizeof(float4) * ntz));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->mats, sizeof(prt_material) * nm));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->light_tris, sizeof(uint32_t) * (nl ? nl : 1)));
+    PRT_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->mats, mats_host, sizeof(prt_material) * nm, cudaMemcpyHostToDevice, s));
+    if (nl) PRT_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->light_tris, light_host, sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, s));
+    if (nt) {
+        unsigned g = (nt + 255) / 256;
+        pack_tris_kernel<<<g, 256, 0, s>>>(verts_dev, tri_mat_dev, nt, ctx->verts_gid);
+        pack_shade_kernel<<<g, 256, 0, s>>>(verts_dev, normals_dev, tri_mat_dev, nt, ctx->shade);
+        PRT_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    PRT_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->nt = nt; ctx->nm = nm; ctx->nl = nl;
+    ctx->scene_set = true;
+    return PRT_OK;
+}
+
+}  // namespace prt
+
+using namespace prt;
+
+#define CHECK_CTX(ctx) \
+    do { if (!(ctx)) return PRT_ERR_INVALID; } while (0)
+#define USE_DEVICE(ctx) PRT_CUDA_TRY(ctx, cudaSetDevice((ctx)->device))
+
+extern "C" {
+
+int prt_abi_version(void) { return PRT_ABI_VERSION; }
+
+int prt_create(int device, prt_ctx** out) {
+    if (!out) { snprintf(g_create_error, sizeof g_create_error, "prt_create: out == NULL"); return PRT_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        snprintf(g_create_error, sizeof g_create_error,
+                 "prt_create: no CUDA device (%s); this library has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return PRT_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        snprintf(g_create_error, sizeof g_create_error, "prt_create: device %d out of range [0,%d)", device, ndev);
+        return PRT_ERR_INVALID;
+    }
+    prt_ctx* c = new (std::nothrow) prt_ctx();
+    if (!c) return PRT_ERR_NOMEM;
+    c->device = device;
+    e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) {
+        c->num_sms = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            snprintf(g_create_error, sizeof g_create_error,
+                     "prt_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+            delete c;
+            return PRT_ERR_CUDA;
+        }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(Counters));
+    if (e == cudaSuccess) e = cudaMemset(c->counters, 0, sizeof(Counters));
+    if (e == cudaSuccess) e = cudaMalloc(&c->flag_count, sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        snprintf(g_create_error, sizeof g_create_error, "prt_create: %s", cudaGetErrorString(e));
+        delete c;
+        return PRT_ERR_CUDA;
+    }
+    *out = c;
+    return PRT_OK;
+}
+
+void prt_destroy(prt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    wavefront_free(ctx);
+    free_scene(ctx);
+    cudaFree(ctx->counters); cudaFree(ctx->flag_list); cudaFree(ctx->flag_count);
+    delete ctx;
+}
+
+const char* prt_last_error(const prt_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int prt_scene_set_triangles(prt_ctx* ctx, const float* verts_host, const float* normals_host,
+                            uint32_t nt, const uint32_t* tri_material_host,
+                            const prt_material* mats_host, uint32_t nm,
+                            const uint32_t* light_tris_host, uint32_t nl) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (nt && !verts_host) { ctx->set_error("scene: verts == NULL"); return PRT_ERR_INVALID; }
+    if (nt >= (1u << 28)) { ctx->set_error("scene: at most 2^28-1 triangles"); return PRT_ERR_INVALID; }
+    if (nl && !light_tris_host) { ctx->set_error("scene: light_tris == NULL"); return PRT_ERR_INVALID; }
+    for (uint32_t i = 0; i < nl; ++i)
+        if (light_tris_host[i] >= nt) { ctx->set_error("scene: light triangle %u out of range", light_tris_host[i]); return PRT_ERR_INVALID; }
+    if (tri_material_host && mats_host)
+        for (uint32_t i = 0; i < nt; ++i)
+            if (tri_material_host[i] >= nm) { ctx->set_error("scene: material index %u out of range", tri_material_host[i]); return PRT_ERR_INVALID; }
+    float *dv = nullptr, *dn = nullptr;
+    uint32_t* dm = nullptr;
+    int rc = PRT_OK;
+    cudaError_t e = cudaSuccess;
+    if (nt) {
+        e = cudaMalloc(&dv, sizeof(float) * 9 * (size_t)nt);
+        if (e == cudaSuccess) e = cudaMemcpy(dv, verts_host, sizeof(float) * 9 * (size_t)nt, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && normals_host) {
+            e = cudaMalloc(&dn, sizeof(float) * 3 * (size_t)nt);
+            if (e == cudaSuccess) e = cudaMemcpy(dn, normals_host, sizeof(float) * 3 * (size_t)nt, cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess && tri_material_host) {
+            e = cudaMalloc(&dm, sizeof(uint32_t) * (size_t)nt);
+            if (e == cudaSuccess) e = cudaMemcpy(dm, tri_material_host, sizeof(uint32_t) * (size_t)nt, cudaMemcpyHostToDevice);
+        }
+    }
+    if (e != cudaSuccess) {
+        ctx->set_error("scene upload: %s", cudaGetErrorString(e));
+        rc = PRT_ERR_CUDA;
+    } else {
+        rc = set_scene_common(ctx, dv, dn, dm, nt, mats_host, nm, light_tris_host, nl, 0);
+    }
+    cudaFree(dv); cudaFree(dn); cudaFree(dm);
+    return rc;
+}
+
+int prt_scene_set_triangles_dev(prt_ctx* ctx, const float* verts_dev, uint32_t nt, void* stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (nt && !verts_dev) { ctx->set_error("scene: verts == NULL"); return PRT_ERR_INVALID; }
+    if (nt >= (1u << 28)) { ctx->set_error("scene: at most 2^28-1 triangles"); return PRT_ERR_INVALID; }
+    return set_scene_common(ctx, verts_dev, nullptr, nullptr, nt, nullptr, 0, nullptr, 0, (cudaStream_t)stream);
+}
+
+int prt_bvh_build(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    return build_bvh(ctx, opts, stats);
+}
+
+int prt_camera_set(prt_ctx* ctx, const prt_camera* cam) {
+    CHECK_CTX(ctx);
+    if (!cam || cam->width == 0 || cam->height == 0) { ctx->set_error("camera: bad argument"); return PRT_ERR_INVALID; }
+    ctx->cam = *cam;
+    ctx->cam_set = true;
+    return PRT_OK;
+}
+
+int prt_generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int jitter, float tmin,
+                      float tmax, prt_ray* rays_dev, void* stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (!rays_dev) { ctx->set_error("generate_rays: rays == NULL"); return PRT_ERR_INVALID; }
+    return generate_rays(ctx, seed, s0, s1, jitter, tmin, tmax, (float4*)rays_dev, (cudaStream_t)stream);
+}
+
+static int trace_common(prt_ctx* ctx, int mode, const prt_ray* rays, uint64_t n, void* o0, void* o1,
+                        uint32_t flags, void* stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (n && (!rays || !o0 || (mode == 2 && !o1))) { ctx->set_error("trace: NULL buffer"); return PRT_ERR_INVALID; }
+    return launch_trace(ctx, mode, (const float4*)rays, n, o0, o1, flags, (cudaStream_t)stream);
+}
+
+int prt_trace_closest(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, prt_hit* hits_dev,
+                      uint32_t flags, void* stream) {
+    return trace_common(ctx, 0, rays_dev, n, hits_dev, nullptr, flags, stream);
+}
+int prt_trace_any(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, uint8_t* occluded_dev,
+                  uint32_t flags, void* stream) {
+    return trace_common(ctx, 1, rays_dev, n, occluded_dev, nullptr, flags, stream);
+}
+int prt_trace_all(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, uint32_t* counts_dev,
+                  uint64_t* sums_dev, uint32_t flags, void* stream) {
+    return trace_common(ctx, 2, rays_dev, n, counts_dev, sums_dev, flags, stream);
+}
+
+int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, prt_hit* hits_host,
+                           uint32_t flags) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (n == 0) return PRT_OK;
+    if (!rays_host || !hits_host) { ctx->set_error("trace_host: NULL buffer"); return PRT_ERR_INVALID; }
+    prt_ray* dr = nullptr;
+    prt_hit* dh = nullptr;
+    cudaError_t e = cudaMalloc(&dr, sizeof(prt_ray) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&dh, sizeof(prt_hit) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dr, rays_host, sizeof(prt_ray) * n, cudaMemcpyHostToDevice);
+    int rc = PRT_OK;
+    if (e == cudaSuccess) rc = launch_trace(ctx, 0, (const float4*)dr, n, dh, nullptr, flags, 0);
+    if (e == cudaSuccess && rc == PRT_OK) e = cudaMemcpy(hits_host, dh, sizeof(prt_hit) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dr); cudaFree(dh);
+    if (e != cudaSuccess) { ctx->set_error("trace_host: %s", cudaGetErrorString(e)); return PRT_ERR_CUDA; }
+    return rc;
+}
+
+int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev, int32_t* prim_ids_dev,
+               void* stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (!params || !accum_dev) { ctx->set_error("render: NULL argument"); return PRT_ERR_INVALID; }
+    return render(ctx, params, accum_dev, prim_ids_dev, (cudaStream_t)stream);
+}
+
+int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (!params || !accum_host) { ctx->set_error("render: NULL argument"); return PRT_ERR_INVALID; }
+    if (!ctx->cam_set) { ctx->set_error("render: camera not set"); return PRT_ERR_STATE; }
+    size_t bytes = sizeof(float) * 4 * (size_t)ctx->cam.width * ctx->cam.height;
+    float* d = nullptr;
+    PRT_CUDA_TRY(ctx, cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpy(d, accum_host, bytes, cudaMemcpyHostToDevice);
+    int rc = PRT_OK;
+    if (e == cudaSuccess) rc = render(ctx, params, d, nullptr, 0);
+    if (e == cudaSuccess && rc == PRT_OK) e = cudaMemcpy(accum_host, d, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->set_error("render_host: %s", cudaGetErrorString(e)); return PRT_ERR_CUDA; }
+    return rc;
+}
+
+int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths) {
+    CHECK_CTX(ctx);
+    if (paths) ctx->wave_paths = paths;
+    return PRT_OK;
+}
+
+int prt_get_counters(prt_ctx* ctx, prt_counters* out) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (!out) { ctx->set_error("counters: out == NULL"); return PRT_ERR_INVALID; }
+    Counters c;
+    PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    PRT_CUDA_TRY(ctx, cudaMemcpy(&c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    out->rays_closest = c.rays_closest; out->rays_shadow = c.rays_shadow;
+    out->node_visits = c.node_visits; out->tri_tests = c.tri_tests;
+    out->flagged_rays = c.flagged_rays; out->paths = c.paths;
+    return PRT_OK;
+}
+
+int prt_reset_counters(prt_ctx* ctx) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    PRT_CUDA_TRY(ctx, cudaMemset(ctx->counters, 0, sizeof(Counters)));
+    return PRT_OK;
+}
+
+int prt_synchronize(prt_ctx* ctx) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    return PRT_OK;
+}
+
+}  // extern "C"

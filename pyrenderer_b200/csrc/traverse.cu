@@ -1,0 +1,162 @@
+// traverse.cu -- API-level trace kernels (prt_trace_closest / _any / _all).
+//
+// One ray per thread, 128-thread CTAs, per-thread short stack in shared memory.
+// EXACT launches are followed by resolve_kernel, which re-traces only the rays
+// whose FP32 decisions were within their error bound, in FP64 with the
+// reference's operation order (see traverse.cuh / intersect.cuh).
+#include "context.cuh"
+#include "traverse.cuh"
+
+namespace prt {
+
+template <bool COUNT>
+__device__ __forceinline__ void flush_counters(Counters* ctr, const TraceResult& r, int mode) {
+    if (!COUNT) return;
+    unsigned long long nn = r.n_nodes, nt = r.n_tris, one = 1;
+    for (int o = 16; o > 0; o >>= 1) {
+        nn += __shfl_down_sync(0xffffffffu, nn, o);
+        nt += __shfl_down_sync(0xffffffffu, nt, o);
+        one += __shfl_down_sync(0xffffffffu, one, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&ctr->node_visits, nn);
+        atomicAdd(&ctr->tri_tests, nt);
+        atomicAdd(mode == MODE_ANY ? &ctr->rays_shadow : &ctr->rays_closest, one);
+    }
+}
+
+template <int MODE, bool EXACT, bool COUNT, bool BRUTE>
+__global__ void __launch_bounds__(kTraceThreads)
+trace_kernel(SceneDev sc, const float4* __restrict__ rays, uint64_t n, void* out0, void* out1,
+             uint32_t* flag_list, unsigned int* flag_count, Counters* ctr) {
+    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    uint64_t i = (uint64_t)blockIdx.x * kTraceThreads + threadIdx.x;
+    TraceResult res;
+    res.n_nodes = 0; res.n_tris = 0;
+    bool active = i < n;
+    if (active) {
+        float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+        trace_one<MODE, EXACT, COUNT, BRUTE>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
+        if (EXACT && res.uncertain) {
+            unsigned int slot = atomicAdd(flag_count, 1u);
+            flag_list[slot] = (uint32_t)i;
+        }
+        if (MODE == MODE_CLOSEST) {
+            prt_hit h;
+            h.t = res.gid >= 0 ? res.t : 0.0f; h.u = res.u; h.v = res.v; h.tri = res.gid;
+            reinterpret_cast<float4*>(out0)[i] =
+                make_float4(h.t, h.u, h.v, __int_as_float(h.tri));
+        } else if (MODE == MODE_ANY) {
+            reinterpret_cast<uint8_t*>(out0)[i] = res.gid >= 0 ? 1 : 0;
+        } else {
+            reinterpret_cast<uint32_t*>(out0)[i] = res.count;
+            reinterpret_cast<unsigned long long*>(out1)[i] = res.sum;
+        }
+    }
+    if (COUNT) {
+        if (!active) { res.n_nodes = 0; res.n_tris = 0; }
+        TraceResult r2 = res;
+        unsigned long long nn = r2.n_nodes, nt = r2.n_tris, one = active ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            nn += __shfl_down_sync(0xffffffffu, nn, o);
+            nt += __shfl_down_sync(0xffffffffu, nt, o);
+            one += __shfl_down_sync(0xffffffffu, one, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&ctr->node_visits, nn);
+            atomicAdd(&ctr->tri_tests, nt);
+            atomicAdd(MODE == MODE_ANY ? &ctr->rays_shadow : &ctr->rays_closest, one);
+        }
+    }
+}
+
+template <int MODE, bool BRUTE>
+__global__ void __launch_bounds__(kTraceThreads)
+resolve_kernel(SceneDev sc, const float4* __restrict__ rays, void* out0, void* out1,
+               const uint32_t* __restrict__ flag_list, const unsigned int* __restrict__ flag_count,
+               Counters* ctr) {
+    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    unsigned int nf = *flag_count;
+    for (unsigned int k = blockIdx.x * kTraceThreads + threadIdx.x; k < nf;
+         k += gridDim.x * kTraceThreads) {
+        uint32_t i = flag_list[k];
+        float4 ro = __ldg(rays + 2ull * i), rd = __ldg(rays + 2ull * i + 1);
+        TraceResult64 res;
+        trace_one_f64<MODE, BRUTE>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
+        if (MODE == MODE_CLOSEST) {
+            float t = res.gid >= 0 ? (float)res.t : 0.0f;
+            reinterpret_cast<float4*>(out0)[i] =
+                make_float4(t, (float)res.u, (float)res.v, __int_as_float(res.gid));
+        } else if (MODE == MODE_ANY) {
+            reinterpret_cast<uint8_t*>(out0)[i] = res.gid >= 0 ? 1 : 0;
+        } else {
+            reinterpret_cast<uint32_t*>(out0)[i] = res.count;
+            reinterpret_cast<unsigned long long*>(out1)[i] = res.sum;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->flagged_rays, (unsigned long long)nf);
+}
+
+template <int MODE, bool EXACT, bool COUNT>
+static void launch2(bool brute, dim3 grid, cudaStream_t s, SceneDev sc, const float4* rays,
+                    uint64_t n, void* o0, void* o1, uint32_t* fl, unsigned int* fc, Counters* c) {
+    if (brute)
+        trace_kernel<MODE, EXACT, COUNT, true><<<grid, kTraceThreads, 0, s>>>(sc, rays, n, o0, o1, fl, fc, c);
+    else
+        trace_kernel<MODE, EXACT, COUNT, false><<<grid, kTraceThreads, 0, s>>>(sc, rays, n, o0, o1, fl, fc, c);
+}
+
+template <int MODE>
+static void launch1(bool exact, bool count, bool brute, dim3 grid, cudaStream_t s, SceneDev sc,
+                    const float4* rays, uint64_t n, void* o0, void* o1, uint32_t* fl,
+                    unsigned int* fc, Counters* c) {
+    if (exact) {
+        if (count) launch2<MODE, true, true>(brute, grid, s, sc, rays, n, o0, o1, fl, fc, c);
+        else launch2<MODE, true, false>(brute, grid, s, sc, rays, n, o0, o1, fl, fc, c);
+    } else {
+        if (count) launch2<MODE, false, true>(brute, grid, s, sc, rays, n, o0, o1, fl, fc, c);
+        else launch2<MODE, false, false>(brute, grid, s, sc, rays, n, o0, o1, fl, fc, c);
+    }
+}
+
+int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* out0, void* out1,
+                 uint32_t flags, cudaStream_t stream) {
+    if (n == 0) return PRT_OK;
+    if (n > (1ull << 31)) { ctx->set_error("trace: n=%llu exceeds 2^31 rays per call", (unsigned long long)n); return PRT_ERR_INVALID; }
+    bool exact = flags & PRT_TRACE_EXACT, count = flags & PRT_TRACE_COUNT, brute = flags & PRT_TRACE_BRUTE;
+    if (!ctx->scene_set) { ctx->set_error("trace: no scene (call prt_scene_set_triangles first)"); return PRT_ERR_STATE; }
+    if (!brute && !ctx->bvh_built) { ctx->set_error("trace: BVH not built (call prt_bvh_build or pass PRT_TRACE_BRUTE)"); return PRT_ERR_STATE; }
+    SceneDev sc = ctx->scene_dev();
+    if (brute) sc.tris = ctx->verts_gid;
+    if (exact && ctx->flag_cap < n) {
+        if (ctx->flag_list) cudaFree(ctx->flag_list);
+        ctx->flag_list = nullptr; ctx->flag_cap = 0;
+        PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->flag_list, n * sizeof(uint32_t)));
+        ctx->flag_cap = n;
+    }
+    if (exact) PRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag_count, 0, sizeof(unsigned int), stream));
+    dim3 grid((unsigned)((n + kTraceThreads - 1) / kTraceThreads));
+    switch (mode) {
+        case MODE_CLOSEST: launch1<MODE_CLOSEST>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;
+        case MODE_ANY: launch1<MODE_ANY>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;
+        default: launch1<MODE_ALL>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;
+    }
+    PRT_CUDA_TRY(ctx, cudaGetLastError());
+    if (exact) {
+        dim3 g2((unsigned)(ctx->num_sms * 4));
+        if (mode == MODE_CLOSEST) {
+            if (brute) resolve_kernel<MODE_CLOSEST, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            else resolve_kernel<MODE_CLOSEST, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+        } else if (mode == MODE_ANY) {
+            if (brute) resolve_kernel<MODE_ANY, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            else resolve_kernel<MODE_ANY, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+        } else {
+            if (brute) resolve_kernel<MODE_ALL, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            else resolve_kernel<MODE_ALL, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+        }
+        PRT_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return PRT_OK;
+}
+
+}  // namespace prt

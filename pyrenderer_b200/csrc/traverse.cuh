@@ -1,0 +1,187 @@
+// traverse.cuh -- one-ray traversal device functions shared by the API trace
+// kernels (traverse.cu) and the wavefront integrator (wavefront.cu).
+#pragma once
+#include "bvh.cuh"
+
+namespace prt {
+
+enum { MODE_CLOSEST = 0, MODE_ANY = 1, MODE_ALL = 2 };
+constexpr unsigned long long kHashMul = 0x9E3779B97F4A7C15ull;
+
+struct TraceResult {
+    float t, u, v, dt;
+    int gid;              // -1 = miss
+    bool uncertain;       // EXACT: needs the FP64 replay
+    uint32_t count;       // MODE_ALL
+    unsigned long long sum;
+    uint32_t n_nodes, n_tris;  // COUNT
+};
+
+template <int MODE, bool EXACT, bool COUNT>
+__device__ __forceinline__ bool process_tris(const SceneDev& sc, const RayW& rw, uint32_t start,
+                                             uint32_t cnt, float tmin, float tmax,
+                                             TraceResult& res) {
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const float4* tp = sc.tris + 3ull * (start + k);
+        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        int gid = __float_as_int(a.w);
+        if (COUNT) ++res.n_tris;
+        TriHit h;
+        bool unc = false;
+        float bound = MODE == MODE_CLOSEST ? res.t : tmax;
+        float berr = MODE == MODE_CLOSEST ? res.dt : 0.0f;
+        int hit = tri_watertight<EXACT>(rw, xyz(a), xyz(b), xyz(c), tmin, bound, berr, h, unc);
+        if (EXACT && unc) { res.uncertain = true; return true; }
+        if (!hit) continue;
+        if (MODE == MODE_CLOSEST) {
+            if (h.t < res.t || gid < res.gid || res.gid < 0) {
+                res.t = h.t; res.u = h.u; res.v = h.v; res.dt = h.dt; res.gid = gid;
+            }
+        } else if (MODE == MODE_ANY) {
+            res.gid = gid; res.t = h.t;
+            return true;
+        } else {
+            ++res.count;
+            res.sum += (unsigned long long)(gid + 1) * kHashMul;
+        }
+    }
+    return false;
+}
+
+// FP32 traversal.  `stack_smem` = &s_stack[0][threadIdx.x].
+template <int MODE, bool EXACT, bool COUNT, bool BRUTE>
+__device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 rd,
+                                          uint32_t* stack_smem, TraceResult& res) {
+    float3 o = xyz(ro), d = xyz(rd);
+    float tmin = ro.w, tmax = rd.w;
+    res.t = tmax; res.u = 0.f; res.v = 0.f; res.dt = 0.f; res.gid = -1;
+    res.uncertain = false; res.count = 0; res.sum = 0ull; res.n_nodes = 0; res.n_tris = 0;
+    RayW rw = make_rayw(o, d);
+    if (BRUTE) {
+        // 7-bit leaf counts do not apply: walk the whole triangle array
+        for (uint32_t s = 0; s < sc.nt; s += 4096u) {
+            uint32_t c = min(4096u, sc.nt - s);
+            if (process_tris<MODE, EXACT, COUNT>(sc, rw, s, c, tmin, tmax, res)) return;
+        }
+        return;
+    }
+    if (sc.n_nodes == 0) return;
+    RayBox rb = make_raybox(o, d);
+    Stack st;
+    st.smem = stack_smem;
+    st.sp = 0;
+    uint32_t cur = 0;
+    while (true) {
+        if (!(cur & kLeafFlag)) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+            if (COUNT) ++res.n_nodes;
+            float t0, t1;
+            float far = MODE == MODE_CLOSEST ? res.t + (EXACT ? res.dt : 0.0f) : tmax;
+            int m = node_test<EXACT>(n0, n1, rb, tmin, far, t0, t1);
+            if (m) {
+                uint32_t r0, r1;
+                node_refs(cur, __float_as_uint(n0.w), __float_as_uint(n1.w), r0, r1);
+                if (m == 3) {
+                    bool swap = MODE == MODE_CLOSEST && t1 < t0;
+                    st.push(swap ? r0 : r1);
+                    cur = swap ? r1 : r0;
+                } else {
+                    cur = (m & 1) ? r0 : r1;
+                }
+                continue;
+            }
+        } else {
+            uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
+            if (process_tris<MODE, EXACT, COUNT>(sc, rw, start, cnt, tmin, tmax, res)) return;
+        }
+        if (st.sp == 0) break;
+        cur = st.pop();
+    }
+}
+
+// FP64 replay: the reference's Moller-Trumbore in double over the same BVH
+// (box culling stays FP32 but is widened by its error bound, so it never
+// rejects a triangle the reference would accept).  Result follows
+// intersection.py:106-116 / scene.py:66-73: min t, lowest GLOBAL id on ties.
+struct TraceResult64 {
+    double t, u, v;
+    int gid;
+    uint32_t count;
+    unsigned long long sum;
+};
+
+template <int MODE>
+__device__ __forceinline__ bool process_tris64(const SceneDev& sc, const double* o, const double* d,
+                                               uint32_t start, uint32_t cnt, double tmin,
+                                               double tmax, TraceResult64& res) {
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const float4* tp = sc.tris + 3ull * (start + k);
+        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        int gid = __float_as_int(a.w);
+        double t, u, v;
+        double bound = MODE == MODE_CLOSEST ? res.t : tmax;
+        if (!mt_f64(xyz(a), xyz(b), xyz(c), o, d, tmin, bound, t, u, v)) continue;
+        if (MODE == MODE_CLOSEST) {
+            if (t < res.t || gid < res.gid || res.gid < 0) { res.t = t; res.u = u; res.v = v; res.gid = gid; }
+        } else if (MODE == MODE_ANY) {
+            res.gid = gid; res.t = t;
+            return true;
+        } else {
+            ++res.count;
+            res.sum += (unsigned long long)(gid + 1) * kHashMul;
+        }
+    }
+    return false;
+}
+
+template <int MODE, bool BRUTE>
+__device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, float4 rd,
+                                              uint32_t* stack_smem, TraceResult64& res) {
+    double o[3] = {(double)ro.x, (double)ro.y, (double)ro.z};
+    double d[3] = {(double)rd.x, (double)rd.y, (double)rd.z};
+    double tmin = (double)ro.w, tmax = (double)rd.w;
+    res.t = tmax; res.u = 0.0; res.v = 0.0; res.gid = -1; res.count = 0; res.sum = 0ull;
+    if (BRUTE) {
+        for (uint32_t s = 0; s < sc.nt; s += 4096u) {
+            uint32_t c = min(4096u, sc.nt - s);
+            if (process_tris64<MODE>(sc, o, d, s, c, tmin, tmax, res)) return;
+        }
+        return;
+    }
+    if (sc.n_nodes == 0) return;
+    RayBox rb = make_raybox(xyz(ro), xyz(rd));
+    Stack st;
+    st.smem = stack_smem;
+    st.sp = 0;
+    uint32_t cur = 0;
+    while (true) {
+        if (!(cur & kLeafFlag)) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+            float t0, t1;
+            float far = MODE == MODE_CLOSEST ? __double2float_ru(res.t) : rd.w;
+            // widen the near side too: tmin enters the slab as a float rounded towards -inf
+            int m = node_test<true>(n0, n1, rb, ro.w, far, t0, t1);
+            if (m) {
+                uint32_t r0, r1;
+                node_refs(cur, __float_as_uint(n0.w), __float_as_uint(n1.w), r0, r1);
+                if (m == 3) {
+                    bool swap = MODE == MODE_CLOSEST && t1 < t0;
+                    st.push(swap ? r0 : r1);
+                    cur = swap ? r1 : r0;
+                } else {
+                    cur = (m & 1) ? r0 : r1;
+                }
+                continue;
+            }
+        } else {
+            uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
+            if (process_tris64<MODE>(sc, o, d, start, cnt, tmin, tmax, res)) return;
+        }
+        if (st.sp == 0) break;
+        cur = st.pop();
+    }
+}
+
+}  // namespace prt

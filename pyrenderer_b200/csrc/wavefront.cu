@@ -1,0 +1,438 @@
+// wavefront.cu -- the wavefront path-tracing integrator.
+//
+// The reference traces one pixel per thread in a megakernel
+// (main_taichi.py:80-99 -> PathTracer.trace core/tracing.py:116-155), or one
+// pixel per joblib task on the CPU (main.py:28-55).  Here a "wave" is up to
+// `wave_paths` paths = k whole samples of every pixel; per bounce four kernels
+// run over device-side queues, all launched with a fixed persistent grid so the
+// host never reads a queue length back:
+//
+//   raygen_kernel    camera rays (core/camera.py:41-72, FP64, bit-equal to the
+//                    oracle's f32 ray records) + path state init
+//   closest_kernel   persistent warps pull 32 queue entries at a time and run the
+//                    closest-hit traversal (traverse.cuh)
+//   shade_kernel     emitter / two-sided flip / cosine or specular sample /
+//                    throughput update / NEE shadow-ray emission / Russian
+//                    roulette; survivors are compacted into the next queue with a
+//                    warp ballot + prefix popcount and ONE atomic per warp
+//   shadow_kernel    any-hit traversal of the shadow queue, adds the pending NEE
+//                    contribution to the path's radiance if unoccluded
+//   advance_kernel   rotates the queue counters (1 thread)
+//   accumulate_kernel  sums the k samples of each pixel in a fixed order and adds
+//                    them to the caller's accumulation buffer (deterministic)
+//
+// The estimator is the reference's, including its quirks:
+// hard-coded light colour for directly seen emitters, cosine-at-light factor
+// after the first bounce, NEE without 1/pi or pdf, one-sided emitter.
+#include "context.cuh"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace prt {
+
+struct WaveState {
+    float4* rays = nullptr;     // [2*cap] by path slot
+    float4* hits = nullptr;     // [cap]
+    float4* beta = nullptr;     // [cap]
+    float4* L = nullptr;        // [cap]
+    float4* srays = nullptr;    // [2*cap] by shadow-queue position
+    float4* scontrib = nullptr; // [cap] rgb + bits(path slot)
+    uint32_t* queue[2] = {nullptr, nullptr};
+    unsigned int* cnt = nullptr;  // [8]: cur, next, shadow, fetch_closest, fetch_shadow
+    uint64_t cap = 0;
+    int grid_trace = 0, grid_shade = 0;
+};
+
+struct CamDev {
+    double m[16];
+    double sw, sh, focal;
+    uint32_t W, H;
+};
+
+struct WaveParams {
+    unsigned long long seed;
+    uint32_t s_begin;      // first sample index of this wave
+    uint32_t ns_wave;      // samples of every pixel in this wave
+    uint32_t npix;
+    uint32_t spp_begin;    // of the whole render call (prim_ids layout)
+    uint32_t ns_total;
+    uint32_t rr_start;
+    float3 light_color;
+    float tmin, tmax;
+};
+
+__device__ __forceinline__ void camera_ray(const CamDev& cam, double u, double v, float4& ro,
+                                           float4& rd, float tmin, float tmax) {
+    // core/camera.py:48-70 in the oracle's operation order (oracle/pt_oracle.c orc_generate_ray)
+    double cs0 = __dsub_rn(u, 0.5), cs1 = __dsub_rn(v, 0.5);
+    double r0 = __ddiv_rn(__dmul_rn(cs0, cam.sw), 0.5), r1 = __ddiv_rn(__dmul_rn(cs1, cam.sh), 0.5);
+    double h0 = (double)__double2float_rn(r0), h1 = (double)__double2float_rn(r1),
+           h2 = (double)__double2float_rn(-cam.focal);
+    double f[3], o[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double dw = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h0, cam.m[j]), __dmul_rn(h1, cam.m[4 + j])),
+                                        __dmul_rn(h2, cam.m[8 + j])), cam.m[12 + j]);
+        o[j] = cam.m[12 + j];
+        f[j] = __dsub_rn(dw, o[j]);
+    }
+    double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(f[0], f[0]), __dmul_rn(f[1], f[1])), __dmul_rn(f[2], f[2])));
+    ro = make_float4(__double2float_rn(o[0]), __double2float_rn(o[1]), __double2float_rn(o[2]), tmin);
+    rd = make_float4(__double2float_rn(__ddiv_rn(f[0], n)), __double2float_rn(__ddiv_rn(f[1], n)),
+                     __double2float_rn(__ddiv_rn(f[2], n)), tmax);
+}
+
+// API-level ray generation: rays[(pixel*ns + s)] for s in [s0,s1)
+__global__ void generate_rays_kernel(CamDev cam, unsigned long long seed, uint32_t s0, uint32_t ns,
+                                     int jitter, float tmin, float tmax, float4* rays) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = (uint64_t)cam.W * cam.H * ns;
+    if (idx >= total) return;
+    uint32_t pixel = (uint32_t)(idx / ns), s = s0 + (uint32_t)(idx % ns);
+    uint32_t i = pixel % cam.W, j = pixel / cam.W;
+    double jx = 0.5, jy = 0.5;
+    if (jitter) {
+        uint4 r = rng4(seed, pixel, s, 0, 0);
+        jx = (double)u24(r.x); jy = (double)u24(r.y);
+    }
+    double u = __ddiv_rn(__dadd_rn((double)i, jx), (double)cam.W);
+    double v = __ddiv_rn(__dadd_rn((double)j, jy), (double)cam.H);
+    float4 ro, rd;
+    camera_ray(cam, u, v, ro, rd, tmin, tmax);
+    rays[2 * idx] = ro;
+    rays[2 * idx + 1] = rd;
+}
+
+__global__ void raygen_kernel(CamDev cam, WaveParams P, float4* rays, float4* beta, float4* L,
+                              uint32_t* queue, unsigned int* cnt) {
+    uint32_t n_paths = P.npix * P.ns_wave;
+    uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid == 0) { cnt[0] = n_paths; cnt[1] = 0; cnt[2] = 0; cnt[3] = 0; cnt[4] = 0; }
+    if (pid >= n_paths) return;
+    uint32_t pixel = pid % P.npix, s = P.s_begin + pid / P.npix;
+    uint32_t i = pixel % cam.W, j = pixel / cam.W;
+    uint4 r = rng4(P.seed, pixel, s, 0, 0);
+    double u = __ddiv_rn(__dadd_rn((double)i, (double)u24(r.x)), (double)cam.W);
+    double v = __ddiv_rn(__dadd_rn((double)j, (double)u24(r.y)), (double)cam.H);
+    float4 ro, rd;
+    camera_ray(cam, u, v, ro, rd, P.tmin, P.tmax);
+    rays[2 * (size_t)pid] = ro;
+    rays[2 * (size_t)pid + 1] = rd;
+    beta[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+    L[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    queue[pid] = pid;
+}
+
+// persistent closest-hit over the current queue
+__global__ void __launch_bounds__(kTraceThreads)
+closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
+               const uint32_t* __restrict__ queue, unsigned int* cnt) {
+    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    const unsigned int n = cnt[0];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cnt + 3, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned int k = base + lane;
+        if (k < n) {
+            uint32_t pid = queue[k];
+            float4 ro = rays[2 * (size_t)pid], rd = rays[2 * (size_t)pid + 1];
+            TraceResult res;
+            trace_one<MODE_CLOSEST, false, false, false>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
+            hits[pid] = make_float4(res.t, res.u, res.v, __int_as_float(res.gid));
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kTraceThreads)
+shadow_kernel(SceneDev sc, const float4* __restrict__ srays, const float4* __restrict__ scontrib,
+              float4* L, unsigned int* cnt) {
+    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    const unsigned int n = cnt[2];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cnt + 4, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned int k = base + lane;
+        if (k < n) {
+            float4 ro = srays[2 * (size_t)k], rd = srays[2 * (size_t)k + 1];
+            TraceResult res;
+            trace_one<MODE_ANY, false, false, false>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
+            if (res.gid < 0) {
+                float4 c = scontrib[k];
+                uint32_t pid = __float_as_uint(c.w);
+                float4 l = L[pid];
+                L[pid] = make_float4(l.x + c.x, l.y + c.y, l.z + c.z, 0.f);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ float guard_beta(float albedo, float cz, float pdf) {
+    // core/tracing.py:145-149
+    float nb = albedo * cz / pdf * kInvPi;
+    if (isnan(nb)) nb = albedo * cz / 1e-4f * kInvPi;
+    return nb;
+}
+
+__global__ void __launch_bounds__(256)
+shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, float4* rays,
+             const float4* __restrict__ hits, float4* beta, float4* L, float4* srays,
+             float4* scontrib, const uint32_t* __restrict__ queue_in, uint32_t* queue_out,
+             unsigned int* cnt, int32_t* prim_ids) {
+    const unsigned int n = cnt[0];
+    const int lane = threadIdx.x & 31;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    // round the loop bound up to a whole warp so ballots see all lanes
+    for (unsigned int k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < n; k0 += stride) {
+        unsigned int k = k0 + lane;
+        bool alive = false, want_shadow = false;
+        uint32_t pid = 0;
+        float4 sro, srd, sc4;
+        if (k < n) {
+            pid = queue_in[k];
+            float4 ro = rays[2 * (size_t)pid], rd = rays[2 * (size_t)pid + 1];
+            float4 h = hits[pid];
+            int gid = __float_as_int(h.w);
+            uint32_t pixel = pid % P.npix, s = P.s_begin + pid / P.npix;
+            if (bounce == 0 && prim_ids)
+                prim_ids[(size_t)pixel * P.ns_total + (s - P.spp_begin)] = gid;
+            if (gid >= 0) {
+                float3 o = xyz(ro), d = xyz(rd);
+                float4 sh = __ldg(sc.shade + gid);
+                float3 n = xyz(sh);
+                const prt_material m = sc.mats[__float_as_uint(sh.w)];
+                float3 b = xyz(beta[pid]);
+                float3 nd = -d;
+                if (m.type == PRT_MAT_EMITTER) {  // core/tracing.py:129-139
+                    float d1 = dot(nd, n);
+                    if (d1 > 0.0f) {
+                        float w = bounce == 0 ? 1.0f : d1;
+                        float4 l = L[pid];
+                        L[pid] = make_float4(l.x + P.light_color.x * b.x * w, l.y + P.light_color.y * b.y * w,
+                                             l.z + P.light_color.z * b.z * w, 0.f);
+                    }
+                } else {
+                    float3 p = make_float3(fmaf(d.x, h.x, o.x), fmaf(d.y, h.x, o.y), fmaf(d.z, h.x, o.z));
+                    bool front = dot(n, nd) >= 0.0f;
+                    if (m.two_sided && !front) n = -n;  // mathematics/shapes.py:99-102
+                    uint4 r1 = rng4(P.seed, pixel, s, bounce, 1);
+                    float3 wi;
+                    bool ok = true, nee = false;
+                    float3 alb = make_float3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                    if (m.type == PRT_MAT_LAMBERT) {
+                        wi = cosine_sample_hemisphere(n, u24(r1.x), u24(r1.y));
+                        float c = dot(n, wi);
+                        float pdf = fabsf(c) * kInvPi;
+                        float cz = fmaxf(c, 0.0f);
+                        b = make_float3(b.x * guard_beta(alb.x, cz, pdf), b.y * guard_beta(alb.y, cz, pdf),
+                                        b.z * guard_beta(alb.z, cz, pdf));
+                        nee = true;
+                    } else {
+                        float3 ns = (!front && !m.two_sided) ? -n : n;
+                        float3 ud = normalize(d);
+                        if (m.type == PRT_MAT_MIRROR) {
+                            wi = reflect(ud, ns);
+                        } else if (m.type == PRT_MAT_CONDUCTOR) {
+                            uint4 r2 = rng4(P.seed, pixel, s, bounce, 2);
+                            wi = reflect(ud, ns) + in_unit_sphere(u24(r1.x), u24(r1.y), u24(r2.z)) * m.roughness;
+                            ok = dot(wi, ns) > 0.0f;  // core/bsdf_taichi.py:58
+                        } else {
+                            float ratio = front ? 1.0f / m.ior : m.ior;
+                            float ct = fminf(-dot(ud, ns), 1.0f);
+                            float st = sqrtf(1.0f - ct * ct);
+                            if (ratio * st > 1.0f || schlick(ct, ratio) > u24(r1.x)) wi = reflect(ud, ns);
+                            else wi = refract(ud, ns, ratio);
+                        }
+                        if (ok) {
+                            wi = normalize(wi);
+                            b = b * alb;
+                        }
+                    }
+                    if (ok) {
+                        if (nee && sc.nl > 0) {  // core/tracing.py:92-108, shapes.py:62-71
+                            uint4 r2 = rng4(P.seed, pixel, s, bounce, 2);
+                            uint32_t lt = sc.light_tris[rand_index(r1.z, sc.nl)];
+                            float su = sqrtf(u24(r2.x)), sv = u24(r2.y);
+                            float a = su * (1.0f - sv), bb = su * sv, c = 1.0f - a - bb;
+                            float3 v0 = xyz(__ldg(sc.verts_gid + 3 * (size_t)lt)),
+                                   v1 = xyz(__ldg(sc.verts_gid + 3 * (size_t)lt + 1)),
+                                   v2 = xyz(__ldg(sc.verts_gid + 3 * (size_t)lt + 2));
+                            float3 p2 = v0 * a + v1 * bb + v2 * c;
+                            float4 lsh = __ldg(sc.shade + lt);
+                            float3 w = p2 - p;
+                            float dist2 = dot(w, w);
+                            float dist = sqrtf(dist2);
+                            w = make_float3(w.x / dist, w.y / dist, w.z / dist);
+                            float dot1 = dot(n, w), dot2 = -dot(xyz(lsh), w);
+                            if (dot1 > 0.0f && dot2 > 0.0f) {
+                                const prt_material lm = sc.mats[__float_as_uint(lsh.w)];
+                                float g = dot1 * dot2 / dist2;
+                                want_shadow = true;
+                                sro = make_float4(p.x, p.y, p.z, P.tmin);
+                                srd = make_float4(w.x, w.y, w.z, dist * (1.0f - 1e-4f));
+                                sc4 = make_float4(b.x * lm.albedo[0] * g, b.y * lm.albedo[1] * g,
+                                                  b.z * lm.albedo[2] * g, __uint_as_float(pid));
+                            }
+                        }
+                        alive = bounce + 1 < max_depth;
+                        if (bounce >= P.rr_start) {
+                            float q = fmaxf(b.x, fmaxf(b.y, b.z));
+                            if (q < 1.0f) {
+                                if (!(u24(r1.w) < q)) alive = false;
+                                else b = make_float3(b.x / q, b.y / q, b.z / q);
+                            }
+                        }
+                        if (alive) {
+                            beta[pid] = make_float4(b.x, b.y, b.z, 0.f);
+                            rays[2 * (size_t)pid] = make_float4(p.x, p.y, p.z, P.tmin);
+                            rays[2 * (size_t)pid + 1] = make_float4(wi.x, wi.y, wi.z, P.tmax);
+                        }
+                    }
+                }
+            }
+        }
+        // warp-aggregated compaction: ballot + prefix popcount, one atomic per warp per queue
+        unsigned int am = __ballot_sync(0xffffffffu, alive);
+        unsigned int sm = __ballot_sync(0xffffffffu, want_shadow);
+        unsigned int abase = 0, sbase = 0;
+        if (lane == 0) {
+            if (am) abase = atomicAdd(cnt + 1, (unsigned int)__popc(am));
+            if (sm) sbase = atomicAdd(cnt + 2, (unsigned int)__popc(sm));
+        }
+        abase = __shfl_sync(0xffffffffu, abase, 0);
+        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        unsigned int lt_mask = (1u << lane) - 1u;
+        if (alive) queue_out[abase + __popc(am & lt_mask)] = pid;
+        if (want_shadow) {
+            unsigned int sk = sbase + __popc(sm & lt_mask);
+            srays[2 * (size_t)sk] = sro;
+            srays[2 * (size_t)sk + 1] = srd;
+            scontrib[sk] = sc4;
+        }
+    }
+}
+
+__global__ void advance_kernel(unsigned int* cnt, Counters* ctr) {
+    atomicAdd(&ctr->rays_closest, (unsigned long long)cnt[0]);
+    atomicAdd(&ctr->rays_shadow, (unsigned long long)cnt[2]);
+    cnt[0] = cnt[1];
+    cnt[1] = 0; cnt[2] = 0; cnt[3] = 0; cnt[4] = 0;
+}
+
+__global__ void accumulate_kernel(const float4* __restrict__ L, uint32_t npix, uint32_t ns_wave,
+                                  float4* accum, Counters* ctr) {
+    uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel == 0) atomicAdd(&ctr->paths, (unsigned long long)npix * ns_wave);
+    if (pixel >= npix) return;
+    float3 s = make_float3(0.f, 0.f, 0.f);
+    for (uint32_t k = 0; k < ns_wave; ++k) {
+        float4 l = L[(size_t)k * npix + pixel];
+        s.x += l.x; s.y += l.y; s.z += l.z;
+    }
+    float4 a = accum[pixel];
+    accum[pixel] = make_float4(a.x + s.x, a.y + s.y, a.z + s.z, a.w + (float)ns_wave);
+}
+
+static CamDev cam_dev(const prt_camera& c) {
+    CamDev d;
+    for (int i = 0; i < 16; ++i) d.m[i] = c.iview[i];
+    d.sw = c.sensor_w; d.sh = c.sensor_h; d.focal = c.focal;
+    d.W = c.width; d.H = c.height;
+    return d;
+}
+
+int generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int jitter, float tmin,
+                  float tmax, float4* rays, cudaStream_t stream) {
+    if (!ctx->cam_set) { ctx->set_error("generate_rays: camera not set"); return PRT_ERR_STATE; }
+    if (s1 <= s0) { ctx->set_error("generate_rays: empty sample range"); return PRT_ERR_INVALID; }
+    uint64_t total = (uint64_t)ctx->cam.width * ctx->cam.height * (s1 - s0);
+    if (total > (1ull << 31)) { ctx->set_error("generate_rays: too many rays for one call"); return PRT_ERR_INVALID; }
+    generate_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cam_dev(ctx->cam), seed, s0, s1 - s0,
+                                                                           jitter, tmin, tmax, rays);
+    PRT_CUDA_TRY(ctx, cudaGetLastError());
+    return PRT_OK;
+}
+
+void wavefront_free(prt_ctx* ctx) {
+    WaveState* w = (WaveState*)ctx->wf;
+    if (!w) return;
+    cudaFree(w->rays); cudaFree(w->hits); cudaFree(w->beta); cudaFree(w->L); cudaFree(w->srays);
+    cudaFree(w->scontrib); cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->cnt);
+    delete w;
+    ctx->wf = nullptr;
+}
+
+static int wave_alloc(prt_ctx* ctx, uint64_t cap) {
+    WaveState* w = (WaveState*)ctx->wf;
+    if (w && w->cap >= cap) return PRT_OK;
+    wavefront_free(ctx);
+    w = new WaveState();
+    ctx->wf = w;
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->rays, sizeof(float4) * 2 * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->hits, sizeof(float4) * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->beta, sizeof(float4) * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->L, sizeof(float4) * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->srays, sizeof(float4) * 2 * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->scontrib, sizeof(float4) * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->queue[0], sizeof(uint32_t) * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->queue[1], sizeof(uint32_t) * cap));
+    PRT_CUDA_TRY(ctx, cudaMalloc(&w->cnt, sizeof(unsigned int) * 8));
+    w->cap = cap;
+    int bt = 0, bs = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, closest_kernel, kTraceThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, shade_kernel, 256, 0);
+    w->grid_trace = ctx->num_sms * (bt > 0 ? bt : 4);
+    w->grid_shade = ctx->num_sms * (bs > 0 ? bs : 4);
+    return PRT_OK;
+}
+
+int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim_ids,
+           cudaStream_t stream) {
+    if (!ctx->scene_set || !ctx->bvh_built) { ctx->set_error("render: scene/BVH not ready"); return PRT_ERR_STATE; }
+    if (!ctx->cam_set) { ctx->set_error("render: camera not set"); return PRT_ERR_STATE; }
+    if (p->spp_end < p->spp_begin) { ctx->set_error("render: spp_end < spp_begin"); return PRT_ERR_INVALID; }
+    if (p->max_depth == 0 || p->spp_end == p->spp_begin) return PRT_OK;
+    const uint64_t npix = (uint64_t)ctx->cam.width * ctx->cam.height;
+    if (npix == 0 || npix > (1ull << 30)) { ctx->set_error("render: bad resolution"); return PRT_ERR_INVALID; }
+    uint64_t per_wave = ctx->wave_paths / npix;
+    if (per_wave == 0) per_wave = 1;
+    const uint32_t ns_total = p->spp_end - p->spp_begin;
+    if (per_wave > ns_total) per_wave = ns_total;
+    int rc = wave_alloc(ctx, npix * per_wave);
+    if (rc != PRT_OK) return rc;
+    WaveState* w = (WaveState*)ctx->wf;
+    SceneDev sc = ctx->scene_dev();
+    CamDev cam = cam_dev(ctx->cam);
+    WaveParams P;
+    P.seed = p->seed; P.npix = (uint32_t)npix; P.spp_begin = p->spp_begin; P.ns_total = ns_total;
+    P.rr_start = p->rr_start;
+    P.light_color = make_float3(p->light_color[0], p->light_color[1], p->light_color[2]);
+    P.tmin = p->tmin; P.tmax = p->tmax;
+    for (uint32_t s = p->spp_begin; s < p->spp_end; s += (uint32_t)per_wave) {
+        P.s_begin = s;
+        P.ns_wave = (uint32_t)((p->spp_end - s) < per_wave ? (p->spp_end - s) : per_wave);
+        uint32_t n_paths = P.npix * P.ns_wave;
+        raygen_kernel<<<(n_paths + 255) / 256, 256, 0, stream>>>(cam, P, w->rays, w->beta, w->L, w->queue[0], w->cnt);
+        for (uint32_t b = 0; b < p->max_depth; ++b) {
+            uint32_t* qin = w->queue[b & 1];
+            uint32_t* qout = w->queue[(b & 1) ^ 1];
+            closest_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt);
+            shade_kernel<<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
+                                                            w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
+            shadow_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->srays, w->scontrib, w->L, w->cnt);
+            advance_kernel<<<1, 1, 0, stream>>>(w->cnt, ctx->counters);
+        }
+        accumulate_kernel<<<(P.npix + 255) / 256, 256, 0, stream>>>(w->L, P.npix, P.ns_wave, (float4*)accum, ctx->counters);
+    }
+    PRT_CUDA_TRY(ctx, cudaGetLastError());
+    return PRT_OK;
+}
+
+}  // namespace prt

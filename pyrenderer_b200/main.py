@@ -1,0 +1,69 @@
+"""Render driver (reference: main.py:40-126 and main_taichi.py:102-127).
+
+    python -m pyrenderer_b200.main [--scene media/cornell_box.json] [--samples 8]
+        [--max-depth 5] [--width W --height H] [--seed 1] [--out test.png]
+
+Loads a Tungsten scene, renders it on the GPU and writes the image the way
+main.py does (row flip, x255 -> uint8; clamped instead of wrapping).
+"""
+import argparse
+import os
+import time
+
+import numpy as np
+
+from .core import tracing
+from .io_utils.read_tungsten import read_file
+
+DEFAULT_SCENE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "media",
+                             "cornell_box.json")
+
+
+def write_png(path, rgb8):
+    """Tiny PNG writer (the reference uses skimage.io.imsave, absent here)."""
+    import struct
+    import zlib
+    h, w, _ = rgb8.shape
+    raw = b"".join(b"\x00" + rgb8[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def main(scene_file=DEFAULT_SCENE, samples=8, max_depth=5, width=None, height=None, seed=1,
+         out="test.png", tonemap=None, device=0):
+    a_scene, a_camera = read_file(scene_file)
+    if width and height:
+        a_camera.resolution = [width, height]
+    import torch
+    t0 = time.time()
+    accum = tracing.render(a_scene, a_camera, spp=samples, max_depth=max_depth, seed=seed,
+                           device=device)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    image = tracing.to_uint8(tracing.to_image(accum, tonemap))
+    if out:
+        write_png(out, image)
+    c = a_scene.commit(device).counters()
+    rays = c["rays_closest"] + c["rays_shadow"]
+    print(f"{samples} spp in {dt:.3f} s  ({samples / dt:.2f} samples/s, {rays / dt / 1e6:.1f} Mrays/s)")
+    return image
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default=DEFAULT_SCENE)
+    ap.add_argument("--samples", type=int, default=8, help="number of spp")
+    ap.add_argument("--max-depth", type=int, default=5)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--out", default="test.png")
+    ap.add_argument("--tonemap", default=None, choices=[None, "sqrt"])
+    a = ap.parse_args()
+    main(a.scene, a.samples, a.max_depth, a.width, a.height, a.seed, a.out, a.tonemap)

@@ -1,0 +1,166 @@
+"""Host-side logic and the C-ABI surface; no GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import CUBE_OBJ, ROOT, SCENE_JSON
+
+
+def test_transforms_match_reference(golden):
+    import json
+    from pyrenderer_b200.mathematics.affine_transformation import make_transformation_matrix
+    data = json.load(open(SCENE_JSON))
+    for k, prim in enumerate(data["primitives"]):
+        m = make_transformation_matrix(prim["transform"])
+        assert np.allclose(m, golden["transforms"][k], rtol=0, atol=1e-15)
+        assert np.linalg.det(m[:3, :3]) > 0
+
+
+def test_loader_counts_and_geometry(golden, cornell):
+    scene, cam = cornell
+    assert scene.vertices.shape == (72, 3) and scene.faces.shape == (36, 3)
+    assert np.allclose(scene.vertices, golden["scene_vertices"], rtol=0, atol=1e-15)
+    assert np.array_equal(scene.faces, golden["scene_faces"])
+    a = scene.arrays()
+    assert np.allclose(a["normals"], golden["scene_normals"], atol=1e-7)
+    assert list(a["light_tris"]) == [34, 35]
+    alb = a["materials"][a["tri_material"]]["albedo"]
+    assert np.allclose(alb, golden["scene_albedo"], atol=1e-7)
+    for k, prim in enumerate(scene.primitives):
+        assert np.allclose(prim.bounds.min_coord, golden["prim_bounds"][k, 0], atol=1e-15)
+        assert np.allclose(prim.bounds.max_coord, golden["prim_bounds"][k, 1], atol=1e-15)
+    # zero-extent ("empty") boxes exactly where the reference's BBox.update_empty says so
+    want = [bool(np.any(np.abs(b[0] - b[1]) <= 1.1754943508222875e-38)) for b in golden["prim_bounds"]]
+    assert [p.bounds.is_empty() for p in scene.primitives] == want
+    assert want[0] and not want[5] and not want[6]
+    assert cam.get_resolution() == [1024, 1024]
+
+
+def test_loader_errors(tmp_path, capsys):
+    import json
+    from pyrenderer_b200.io_utils.read_tungsten import read_file
+    base = json.load(open(SCENE_JSON))
+    bad = dict(base)
+    bad["primitives"] = base["primitives"] + [{"type": "sphere", "bsdf": "Floor", "transform": {}}]
+    p = tmp_path / "s.json"
+    p.write_text(json.dumps(bad))
+    scene, _ = read_file(str(p))
+    assert "[WARNING] sphere not implemented" in capsys.readouterr().out
+    assert len(scene.primitives) == 8
+    bad2 = dict(base)
+    bad2["bsdfs"] = base["bsdfs"] + [{"name": "x", "type": "plastic", "albedo": 1}]
+    p.write_text(json.dumps(bad2))
+    with pytest.raises(NotImplementedError):
+        read_file(str(p))
+
+
+def test_camera_matches_reference(golden):
+    from pyrenderer_b200.core.camera import Camera
+    cams = [dict(position=[0, 1, 6.8], looking_at=[0, 1, 0], up=[0, 1, 0], resolution=[1024, 1024], fov=19.5),
+            dict(position=[2.6, 2.1, 3.4], looking_at=[0.5, 0.5, 0.5], up=[0, 1, 0], resolution=[640, 480], fov=35.0)]
+    for ci, kw in enumerate(cams):
+        cam = Camera(**kw)
+        assert np.allclose(cam.iview, golden[f"cam{ci}_iview"], rtol=0, atol=1e-15)
+        for uv, want in zip(golden["cam_uv"][:64], golden[f"cam{ci}_rays"][:64]):
+            r = cam.generate_ray(uv)
+            assert np.allclose(r.position, want[:3], atol=1e-15)
+            assert np.allclose(r.direction, want[3:], atol=1e-15)
+
+
+def test_exr_light_mask(golden, cornell):
+    """the pixels of TungstenRender.exr that equal the emission (17,12,4)
+    must lie inside the light-quad mask of the restated camera (pins look_at / fov /
+    aspect / row flip)."""
+    scene, cam = cornell
+    a = scene.arrays()
+    W = H = 1024
+    sw, sh = cam.sensor()
+    ocam = oracle.make_camera(cam.iview, sw, sh, 1.0, W, H)
+    rows, cols = golden["exr_light_rows"].astype(int), golden["exr_light_cols"].astype(int)
+    assert rows.size == 4464
+    r0, r1, c0, c1 = rows.min() - 3, rows.max() + 4, cols.min() - 3, cols.max() + 4
+    jj, ii = np.meshgrid(np.arange(r0, r1), np.arange(c0, c1), indexing="ij")
+    rays = np.empty((jj.size, 8), np.float32)
+    for k, (row, col) in enumerate(zip(jj.ravel(), ii.ravel())):
+        # image row 0 is the top: v = (H-1-row + 0.5)/H   (main.py:55 row flip)
+        o, d = oracle.generate_ray(ocam, (col + 0.5) / W, (H - 1 - row + 0.5) / H)
+        rays[k] = [*o, 1e-5, *d, 99999.9]
+    ids, _, _, _ = oracle.closest_hit(a["tris"], rays)
+    mask = np.isin(ids, [34, 35]).reshape(jj.shape)
+    exr = np.zeros_like(mask)
+    exr[rows - r0, cols - c0] = True
+    assert not np.any(exr & ~mask), "EXR light pixels outside the restated light mask"
+    iou = (exr & mask).sum() / (exr | mask).sum()
+    assert iou > 0.88
+    ys, xs = np.nonzero(mask)
+    assert abs((ys.min() + r0) - rows.min()) <= 2 and abs((xs.max() + c0) - cols.max()) <= 2
+
+
+def test_obj_loader():
+    from pyrenderer_b200.io_utils.read_tungsten import read_obj
+    v, f = read_obj(CUBE_OBJ)
+    assert v.shape == (8, 3) and f.shape == (12, 3)
+    assert v.min() == 0.0 and v.max() == 1.0
+    assert list(f[0]) == [0, 6, 4]
+
+
+def test_sample_sharding():
+    from pyrenderer_b200.core.tracing import shard_samples
+    for spp in (1, 7, 16, 1024):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [shard_samples(spp, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == spp
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """libprt.so loads without a GPU and exports exactly what include/prt.h declares."""
+    from pyrenderer_b200 import _abi, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "prt.h")).read()
+    declared = sorted(set(re.findall(r"\b(prt_[a-z_]+)\s*\(", header)))
+    assert declared == sorted(_abi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.prt_abi_version() == 1
+
+
+def test_abi_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pyrenderer_b200 import _abi
+    with pytest.raises(_abi.PrtError) as e:
+        _abi.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_struct_layouts_match_oracle():
+    from pyrenderer_b200 import _abi
+    assert _abi.MATERIAL_DTYPE == oracle.MATERIAL_DTYPE
+    assert ctypes.sizeof(_abi.PrtCamera) == ctypes.sizeof(oracle.Camera) == 160
+    assert ctypes.sizeof(_abi.PrtRenderParams) == ctypes.sizeof(oracle.RenderParams) == 48
+    assert _abi.HIT_DTYPE.itemsize == 16
+
+
+def test_oracle_light_hit_known_answer(cornell):
+    """a primary ray that hits the light returns exactly light_color."""
+    scene, cam = cornell
+    a = scene.arrays()
+    sw, sh = cam.sensor()
+    W = H = 64
+    ocam = oracle.make_camera(cam.iview, sw, sh, 1.0, W, H)
+    P = oracle.make_params(seed=3, spp_begin=0, spp_end=4, max_depth=5)
+    acc, ids, stats = oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"],
+                                    a["light_tris"], ocam, P, want_ids=True)
+    on_light = np.all(np.isin(ids, [34, 35]), axis=2)
+    assert on_light.sum() >= 10
+    mean = acc[..., :3] / acc[..., 3:]
+    assert np.allclose(mean[on_light], np.array([0.9, 0.85, 0.7], np.float32).astype(np.float64), atol=1e-12)
+    assert stats[0] > W * H * 4 and stats[1] > 0
+    assert np.all(mean >= 0) and np.isfinite(mean).all()

@@ -1,0 +1,131 @@
+"""The CPU oracle (oracle/pt_oracle.c) against fixtures produced by the
+REFERENCE's own code (tests/golden/make_golden.py).  No GPU needed."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import make_rays
+
+F32MAX = 3.4028234663852886e+38
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in oracle.philox4x32_10(ctr, key)) == want
+
+
+@pytest.mark.parametrize("case", ["cornell", "soup64"])
+def test_closest_hit_matches_reference_grouped_kernel(golden, case):
+    """ids AND t bit-exact vs mathematics/intersection.py:68-118 (numba, f64)."""
+    tris = golden[f"ch_{case}_tris"]
+    rays = make_rays(golden[f"ch_{case}_o"], golden[f"ch_{case}_d"], tmin=1.1754943508222875e-38,
+                     tmax=F32MAX)
+    ids, t, _, _ = oracle.closest_hit(tris, rays)
+    assert np.array_equal(ids, golden[f"ch_{case}_ids"])
+    hit = ids >= 0
+    assert hit.sum() > 100
+    assert np.array_equal(t[hit], golden[f"ch_{case}_t"][hit])
+
+
+def test_scalar_kernel_decisions(golden):
+    """Decisions of intersection.py:7-39 (np.cross/np.dot) == oracle scalar port; t to 1e-12
+    (BLAS dot vs explicit sums differ in the last bits -- SURVEY B.4)."""
+    tris = golden["ch_soup64_tris"].astype(np.float64)
+    o = golden["ch_soup64_o"][:300].astype(np.float64)
+    d = golden["ch_soup64_d"][:300].astype(np.float64)
+    dec, tt = golden["scalar_dec"], golden["scalar_t"]
+    for i in range(0, 300, 3):
+        for k in range(64):
+            hit, t = oracle.mt_scalar(tris[k, 0], tris[k, 1], tris[k, 2], o[i], d[i])
+            assert hit == bool(dec[i, k])
+            if hit:
+                assert abs(t - tt[i, k]) <= 1e-12 * max(1.0, abs(t))
+
+
+def test_grouped_and_scalar_agree(golden):
+    """the reference's two formulations accept the same set."""
+    tris = golden["ch_soup64_tris"]
+    rays = make_rays(golden["ch_soup64_o"][:300], golden["ch_soup64_d"][:300], tmin=1.1754943508222875e-38, tmax=F32MAX)
+    cnt, _ = oracle.all_hits(tris, rays)
+    assert np.array_equal(cnt, golden["scalar_dec"].sum(axis=1))
+
+
+def test_slab(golden):
+    g = golden
+    for i in range(g["slab_o"].shape[0]):
+        hit, t0 = oracle.slab(0.0, F32MAX, g["slab_o"][i], g["slab_inv"][i], g["slab_bmin"][i], g["slab_bmax"][i])
+        assert hit == (g["slab_res"][i, 0] > 0)
+        if hit:
+            assert t0 == g["slab_res"][i, 1]
+
+
+def test_concentric_disk(golden):
+    for u, want in zip(golden["disk_u"], golden["disk_res"]):
+        got = oracle.concentric_sample_disk(u[0], u[1])
+        assert np.allclose(got, want, rtol=0, atol=1e-15)
+
+
+def test_frame_and_cosine_sample(golden):
+    for n, want in zip(golden["frame_n"], golden["frame_res"]):
+        r1, r2, r3 = oracle.frame_z_to(n)
+        assert np.allclose(np.stack([r1, r2, r3]), want, rtol=0, atol=1e-15)
+    for i, n in enumerate(golden["frame_n"]):
+        u = golden["disk_u"][i]
+        got = oracle.cosine_sample_hemisphere(n, u[0], u[1])
+        assert np.allclose(got, golden["cos_res"][i], rtol=0, atol=1e-14)
+        assert np.dot(got, n / np.linalg.norm(n)) >= -1e-12
+
+
+def test_camera(golden):
+    from math import radians, tan
+    specs = [(19.5, 1024, 1024), (35.0, 640, 480)]
+    for ci, (fov, w, h) in enumerate(specs):
+        sh = tan(radians(fov) / 2) * 1.0
+        cam = oracle.make_camera(golden[f"cam{ci}_iview"], sh * (w / h * 1.0), sh, 1.0, w, h)
+        for uv, want in zip(golden["cam_uv"], golden[f"cam{ci}_rays"]):
+            o, d = oracle.generate_ray(cam, uv[0], uv[1])
+            assert np.allclose(o, want[:3], rtol=0, atol=1e-15)
+            if ci == 0:  # Cornell camera (pure translation): bit-exact in f64
+                assert np.array_equal(d, want[3:])
+            # rotated camera: numpy's BLAS matmul sums in another order -> <= 2 ulp(f64);
+            # the f32 ray record that crosses the device boundary is identical
+            assert np.allclose(d, want[3:], rtol=0, atol=1e-15)
+            assert np.array_equal(d.astype(np.float32), want[3:].astype(np.float32))
+
+
+def test_golden_path_of_reference_test_py(golden, cornell):
+    """test.py:38-57: 9 recorded bounces.  Through the oracle on the restated loader's
+    geometry: expected triangle ids, |dt| <= 5e-6, normals, albedo."""
+    scene, _ = cornell
+    a = scene.arrays()
+    gp, rep = golden["golden_path"], golden["golden_path_replay"]
+    want_ids = [4, 7, 5, 23, 4, 1, 7, 1, 7]
+    rays = make_rays(gp[:, 1:4], gp[:, 4:7], tmin=1e-5, tmax=999.9)
+    ids, t, _, _ = oracle.closest_hit(a["tris"], rays)
+    assert list(ids) == want_ids
+    assert np.all(np.abs(t - gp[:, 0]) <= 5e-6)
+    # The reference's own replay (its NumPy Scene.hit, f64 geometry).  Row 3 starts exactly
+    # on the back wall and the reference self-hits it at t ~ 2e-17 because its lower bound is
+    # EPS = 1.18e-38 (SURVEY App. A.1 hazard); the recorded path and the oracle use t_min = 1e-5.
+    ok = rep[:, 0] > 1e-5
+    assert list(np.nonzero(~ok)[0]) == [3]
+    assert np.all(np.abs(t - rep[:, 0])[ok] <= 1e-6)
+    for k, tri in enumerate(ids):
+        n = a["normals"][tri].astype(np.float64)
+        if np.dot(n, -gp[k, 4:7]) < 0:
+            n = -n
+        assert np.allclose(n, gp[k, 13:16], atol=1.5e-6)
+        if ok[k]:
+            assert np.allclose(n, rep[k, 1:4], atol=1e-6)
+        alb = a["materials"][a["tri_material"][tri]]["albedo"]
+        assert np.allclose(alb, gp[k, 10:13], atol=1e-6)
+        if ok[k]:
+            assert np.allclose(alb, rep[k, 4:7], atol=1e-6)
+    # row k+1 starts where row k ended
+    for k in range(8):
+        assert np.allclose(gp[k, 1:4] + t[k] * gp[k, 4:7], gp[k + 1, 1:4], atol=2e-5)
