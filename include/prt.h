@@ -90,8 +90,11 @@ typedef struct {
     uint32_t rr_start;    /* first bounce with Russian roulette; 0xffffffff = off (reference) */
     float light_color[3]; /* core/tracing.py:120 */
     float tmin, tmax;     /* core/tracing.py:127 */
-    uint32_t flags;       /* reserved, 0 */
+    uint32_t flags;       /* PRT_RENDER_* */
 } prt_render_params;
+
+/* bounce-0 closest hit runs in PRT_TRACE_EXACT mode: primary-hit ids bit-exact */
+#define PRT_RENDER_EXACT_PRIMARY 1u
 
 typedef struct {
     uint32_t n_tris, n_nodes, depth, max_leaf_tris;

@@ -1,0 +1,34 @@
+"""Small driver for ncu: 1M-triangle soup, closest-hit batches of 2^22 incoherent rays.
+usage: python profiles/prof_trace.py [n_launches]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import soup  # noqa: E402
+from pyrenderer_b200 import _abi  # noqa: E402
+
+n_launch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+N = 1 << 22
+dev = torch.device("cuda", 0)
+ctx = _abi.Context(0)
+ctx.set_triangles_dev(torch.from_numpy(soup(1_000_000)).to(dev), 1_000_000)
+print(ctx.build_bvh())
+g = torch.Generator(device=dev)
+g.manual_seed(11)
+r = torch.empty((N, 8), dtype=torch.float32, device=dev)
+r[:, 0:3] = torch.rand((N, 3), generator=g, device=dev)
+d = torch.randn((N, 3), generator=g, device=dev)
+r[:, 4:7] = d / d.norm(dim=1, keepdim=True)
+r[:, 3] = 1e-5
+r[:, 7] = 3.4e38
+hits = torch.empty((N, 4), dtype=torch.float32, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(n_launch):
+    e0.record()
+    ctx.trace_closest(r, N, hits, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"launch {i}: {e0.elapsed_time(e1):.3f} ms  {N / e0.elapsed_time(e1) / 1e3:.1f} Mrays/s")

@@ -20,6 +20,7 @@ MATERIAL_DTYPE = np.dtype(
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 
 TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE = 1, 2, 4
+RENDER_EXACT_PRIMARY = 1
 
 
 class PrtCamera(C.Structure):
@@ -209,7 +210,12 @@ class Context:
 
     def trace_closest_host(self, rays, flags=0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
-        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        if rays.shape[0] >= (1 << 16):  # big batches: page-locked result buffer (async D2H)
+            import torch
+            hits = torch.empty((rays.shape[0], 4), dtype=torch.float32, pin_memory=True).numpy()
+            hits = hits.view(HIT_DTYPE).reshape(rays.shape[0])
+        else:
+            hits = np.empty(rays.shape[0], HIT_DTYPE)
         self._check(self.lib.prt_trace_closest_host(self.h, _np_ptr(rays), rays.shape[0], _np_ptr(hits),
                                                     int(flags)))
         return hits
@@ -217,13 +223,13 @@ class Context:
     # -- render ---------------------------------------------------------------
     @staticmethod
     def render_params(seed=1, spp_begin=0, spp_end=1, max_depth=5, rr_start=0xFFFFFFFF,
-                      light_color=(0.9, 0.85, 0.7), tmin=1e-5, tmax=99999.9):
+                      light_color=(0.9, 0.85, 0.7), tmin=1e-5, tmax=99999.9, flags=0):
         p = PrtRenderParams()
         p.seed, p.spp_begin, p.spp_end = int(seed), int(spp_begin), int(spp_end)
         p.max_depth, p.rr_start = int(max_depth), int(rr_start)
         for k in range(3):
             p.light_color[k] = float(light_color[k])
-        p.tmin, p.tmax, p.flags = float(tmin), float(tmax), 0
+        p.tmin, p.tmax, p.flags = float(tmin), float(tmax), int(flags)
         return p
 
     def render(self, params, accum_dev, prim_ids_dev=None, stream=None):

@@ -27,7 +27,8 @@ def new_accum(camera, device=0):
 
 
 def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_OFF, device=0,
-           accum=None, want_prim_ids=False, light_color=LIGHT_COLOR, stream=None):
+           accum=None, want_prim_ids=False, light_color=LIGHT_COLOR, stream=None,
+           exact_primary=False):
     """Add samples [spp_begin, spp_begin+spp) to ``accum`` (created if None).
 
     Returns ``accum`` (torch f32 [h, w, 4]: rgb sums + sample count, row 0 = bottom
@@ -44,7 +45,7 @@ def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_O
         ids = torch.full((h, w, spp), -2, dtype=torch.int32, device=accum.device)
     params = ctx.render_params(seed=seed, spp_begin=spp_begin, spp_end=spp_begin + spp,
                                max_depth=max_depth, rr_start=rr_start, light_color=light_color,
-                               tmin=T_MIN, tmax=T_MAX)
+                               tmin=T_MIN, tmax=T_MAX, flags=1 if exact_primary else 0)
     ctx.render(params, accum, ids, stream)
     return (accum, ids) if want_prim_ids else accum
 
@@ -55,14 +56,18 @@ def shard_samples(spp, rank, world):
 
 
 def render_distributed(scene, camera, spp, max_depth=5, seed=1, rr_start=RR_OFF, device=0,
-                       accum=None, group=None):
-    """Every rank renders its sample shard; one all-reduce sums the buffers."""
+                       accum=None, group=None, render_fn=None):
+    """Every rank renders its sample shard; one all-reduce sums the buffers.
+
+    ``render_fn`` (default :func:`render`) exists so the sharding + reduction logic can be
+    exercised without a GPU (tests/test_distributed_cpu.py plugs the CPU oracle in over gloo).
+    """
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     s0, s1 = shard_samples(spp, rank, world)
-    accum = render(scene, camera, spp=s1 - s0, max_depth=max_depth, seed=seed, spp_begin=s0,
-                   rr_start=rr_start, device=device, accum=accum)
+    accum = (render_fn or render)(scene, camera, spp=s1 - s0, max_depth=max_depth, seed=seed,
+                                  spp_begin=s0, rr_start=rr_start, device=device, accum=accum)
     if world > 1:
         dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
     return accum

@@ -35,6 +35,16 @@ struct prt_ctx {
     uint32_t* flag_list = nullptr;
     unsigned int* flag_count = nullptr;
     uint64_t flag_cap = 0;
+    static constexpr unsigned kFetchRing = 32;
+    unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
+    unsigned fetch_next = 0;
+    int grid_persist = 0;
+
+    // device staging of the *_host entry points (grow-only, reused across calls)
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_bytes[2] = {0, 0};
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t copy_event[4] = {nullptr, nullptr, nullptr, nullptr};
 
     // wavefront state (wavefront.cu)
     void* wf = nullptr;

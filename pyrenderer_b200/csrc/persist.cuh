@@ -1,0 +1,160 @@
+// persist.cuh -- persistent-warp FP32 traversal with lane-level dynamic ray fetch.
+//
+// Incoherent rays have very different traversal lengths (soup-1M: mean 83 node
+// visits, long tail).  With one ray per thread a warp runs until its LONGEST ray
+// ends; ncu measured 6.7 of 32 lanes active (profiles/r1_trace_kernel_ncu.txt).
+// Here warps are persistent: whenever fewer than `kRefillBelow` lanes still hold a
+// ray, the idle lanes pull new rays from a global counter (one atomic per warp,
+// ballot + prefix popcount for the slot), after Aila & Laine, "Understanding the
+// efficiency of ray traversal on GPUs" (HPG 2009).  Inside, the loop is
+// while-while: every lane walks internal records until it reaches a leaf, then the
+// warp intersects leaves together.
+//
+// IO is a functor: load(k, ro, rd, tag) / store(tag, t, u, v, gid); it is what
+// binds this loop to the API ray arrays or to the wavefront queues.
+#pragma once
+#include "bvh.cuh"
+#include "traverse.cuh"
+
+namespace prt {
+
+constexpr int kRefillBelow = 22;
+constexpr uint32_t kDone = 0xFFFFFFFFu;  // has kLeafFlag set: ends the node phase
+
+__device__ __forceinline__ void sstack_push(uint32_t saddr, uint32_t* ovf, int& sp, uint32_t v) {
+    if (sp < kSmemStack) asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 4u)), "r"(v) : "memory");
+    else ovf[sp - kSmemStack] = v;
+    ++sp;
+}
+__device__ __forceinline__ uint32_t sstack_pop(uint32_t saddr, const uint32_t* ovf, int& sp) {
+    --sp;
+    uint32_t v;
+    if (sp < kSmemStack) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + (uint32_t)sp * (kTraceThreads * 4u)) : "memory");
+    else v = ovf[sp - kSmemStack];
+    return v;
+}
+
+template <int MODE, bool COUNT, class IO>
+__device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsigned int* fetch,
+                                                 unsigned int n, uint32_t* stack_col, Counters* ctr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
+    uint32_t ovf[kMaxStack - kSmemStack];
+    bool has_ray = false, exhausted = (sc.n_nodes == 0);
+    // per-ray state
+    RayW rw;
+    RayBox rb;
+    float tmin = 0.f, tmax = 0.f, bt = 0.f, bu = 0.f, bv = 0.f;
+    int bgid = -1, sp = 0;
+    uint32_t cur = kDone, tag = 0;
+    unsigned long long c_nodes = 0, c_tris = 0, c_rays = 0;
+
+    if (sc.n_nodes == 0) {  // empty scene: everything misses
+        for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            float4 ro, rd;
+            io.load(k, ro, rd, tag);
+            io.store(tag, rd.w, 0.f, 0.f, -1);
+        }
+        return;
+    }
+
+    while (true) {
+        unsigned idle = __ballot_sync(FULL, !has_ray);
+        if (idle && !exhausted) {
+            unsigned base = 0;
+            const int leader = __ffs(idle) - 1, nidle = __popc(idle);
+            if (lane == leader) base = atomicAdd(fetch, (unsigned)nidle);
+            base = __shfl_sync(FULL, base, leader);
+            if (!has_ray) {
+                unsigned k = base + __popc(idle & lt);
+                if (k < n) {
+                    float4 ro, rd;
+                    io.load(k, ro, rd, tag);
+                    float3 o = xyz(ro), d = xyz(rd);
+                    rw = make_rayw(o, d);
+                    rb = make_raybox(o, d);
+                    tmin = ro.w; tmax = rd.w;
+                    bt = tmax; bu = 0.f; bv = 0.f; bgid = -1;
+                    cur = 0; sp = 0;
+                    has_ray = true;
+                    if (COUNT) ++c_rays;
+                }
+            }
+            if (base + (unsigned)nidle >= n) exhausted = true;
+        }
+        if (__ballot_sync(FULL, has_ray) == 0) break;
+        const int thresh = exhausted ? 1 : kRefillBelow;
+
+        while (true) {
+            if (has_ray) {
+                // ---- node phase: walk internal records until a leaf (or the end)
+                while (!(cur & kLeafFlag)) {
+                    const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+                    if (COUNT) ++c_nodes;
+                    float t0, t1;
+                    const int m = node_test<false>(n0, n1, rb, tmin, MODE == MODE_CLOSEST ? bt : tmax, t0, t1);
+                    // child references, branch-free (layout: bvh.cuh header)
+                    const uint32_t em = __float_as_uint(n0.w), link = __float_as_uint(n1.w);
+                    const uint32_t c0 = (em >> 24) & 0xFu, c1 = em >> 28;
+                    const uint32_t leaf0 = kLeafFlag | (link << 3) | c0;
+                    const uint32_t leaf1 = kLeafFlag | ((link + c0) << 3) | c1;  // c0 == 0 when child0 is internal
+                    const uint32_t r0 = c0 ? leaf0 : cur + 1;
+                    const uint32_t r1 = c1 ? leaf1 : (c0 ? cur + 1 : link);
+                    if (m == 3) {
+                        const bool swap = MODE == MODE_CLOSEST && t1 < t0;
+                        sstack_push(saddr, ovf, sp, swap ? r0 : r1);
+                        cur = swap ? r1 : r0;
+                    } else if (m) {
+                        cur = (m & 1) ? r0 : r1;
+                    } else {
+                        cur = sp ? sstack_pop(saddr, ovf, sp) : kDone;
+                    }
+                }
+                // ---- leaf phase
+                if (cur != kDone) {
+                    const uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
+                    bool stop = false;
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const float4* tp = sc.tris + 3ull * (start + k);
+                        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        if (COUNT) ++c_tris;
+                        TriHit h;
+                        bool unc;
+                        if (tri_watertight<false>(rw, xyz(a), xyz(b), xyz(c), tmin, MODE == MODE_CLOSEST ? bt : tmax, 0.f, h, unc)) {
+                            const int gid = __float_as_int(a.w);
+                            if (MODE == MODE_CLOSEST) {
+                                if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; }
+                            } else {
+                                bt = h.t; bgid = gid; stop = true;
+                                break;
+                            }
+                        }
+                    }
+                    cur = (!stop && sp) ? sstack_pop(saddr, ovf, sp) : kDone;
+                }
+                if (cur == kDone) {
+                    io.store(tag, bt, bu, bv, bgid);
+                    has_ray = false;
+                }
+            }
+            if (__popc(__ballot_sync(FULL, has_ray)) < thresh) break;
+        }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            c_nodes += __shfl_down_sync(FULL, c_nodes, o);
+            c_tris += __shfl_down_sync(FULL, c_tris, o);
+            c_rays += __shfl_down_sync(FULL, c_rays, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&ctr->node_visits, c_nodes);
+            atomicAdd(&ctr->tri_tests, c_tris);
+            atomicAdd(MODE == MODE_ANY ? &ctr->rays_shadow : &ctr->rays_closest, c_rays);
+        }
+    }
+}
+
+}  // namespace prt

@@ -122,6 +122,7 @@ int prt_create(int device, prt_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(Counters));
     if (e == cudaSuccess) e = cudaMemset(c->counters, 0, sizeof(Counters));
     if (e == cudaSuccess) e = cudaMalloc(&c->flag_count, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->fetch_counters, sizeof(unsigned int) * prt_ctx::kFetchRing);
     if (e != cudaSuccess) {
         snprintf(g_create_error, sizeof g_create_error, "prt_create: %s", cudaGetErrorString(e));
         delete c;
@@ -137,6 +138,9 @@ void prt_destroy(prt_ctx* ctx) {
     wavefront_free(ctx);
     free_scene(ctx);
     cudaFree(ctx->counters); cudaFree(ctx->flag_list); cudaFree(ctx->flag_count);
+    cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]); cudaFree(ctx->fetch_counters);
+    for (auto& s : ctx->copy_stream) if (s) cudaStreamDestroy(s);
+    for (auto& e : ctx->copy_event) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -233,23 +237,55 @@ int prt_trace_all(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, uint32_t* c
     return trace_common(ctx, 2, rays_dev, n, counts_dev, sums_dev, flags, stream);
 }
 
+static int stage_reserve(prt_ctx* ctx, int which, size_t bytes) {
+    if (ctx->stage_bytes[which] >= bytes) return PRT_OK;
+    cudaFree(ctx->stage[which]);
+    ctx->stage[which] = nullptr; ctx->stage_bytes[which] = 0;
+    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->stage[which], bytes));
+    ctx->stage_bytes[which] = bytes;
+    return PRT_OK;
+}
+
+// Host-buffer closest hit: rays are cut into chunks and pipelined over two streams so that
+// the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the traversal of chunk k.
 int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, prt_hit* hits_host,
                            uint32_t flags) {
     CHECK_CTX(ctx);
     USE_DEVICE(ctx);
     if (n == 0) return PRT_OK;
     if (!rays_host || !hits_host) { ctx->set_error("trace_host: NULL buffer"); return PRT_ERR_INVALID; }
-    prt_ray* dr = nullptr;
-    prt_hit* dh = nullptr;
-    cudaError_t e = cudaMalloc(&dr, sizeof(prt_ray) * n);
-    if (e == cudaSuccess) e = cudaMalloc(&dh, sizeof(prt_hit) * n);
-    if (e == cudaSuccess) e = cudaMemcpy(dr, rays_host, sizeof(prt_ray) * n, cudaMemcpyHostToDevice);
-    int rc = PRT_OK;
-    if (e == cudaSuccess) rc = launch_trace(ctx, 0, (const float4*)dr, n, dh, nullptr, flags, 0);
-    if (e == cudaSuccess && rc == PRT_OK) e = cudaMemcpy(hits_host, dh, sizeof(prt_hit) * n, cudaMemcpyDeviceToHost);
-    cudaFree(dr); cudaFree(dh);
-    if (e != cudaSuccess) { ctx->set_error("trace_host: %s", cudaGetErrorString(e)); return PRT_ERR_CUDA; }
-    return rc;
+    const uint64_t chunk = 1ull << 21;
+    const uint64_t cap = n < 2 * chunk ? n : 2 * chunk;  // two chunks in flight
+    int rc = stage_reserve(ctx, 0, sizeof(prt_ray) * cap);
+    if (rc == PRT_OK) rc = stage_reserve(ctx, 1, sizeof(prt_hit) * cap);
+    if (rc != PRT_OK) return rc;
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->copy_stream[k]) PRT_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream[k], cudaStreamNonBlocking));
+    prt_ray* dr = (prt_ray*)ctx->stage[0];
+    prt_hit* dh = (prt_hit*)ctx->stage[1];
+    // EXACT shares one flag list per context -> keep exact launches on one stream
+    const bool serial = (flags & PRT_TRACE_EXACT) != 0;
+    uint64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        uint64_t m = n - done < chunk ? n - done : chunk;
+        cudaStream_t s = ctx->copy_stream[serial ? 0 : slot];
+        uint64_t off = (cap == n) ? done : (uint64_t)slot * chunk;
+        PRT_CUDA_TRY(ctx, cudaMemcpyAsync(dr + off, rays_host + done, sizeof(prt_ray) * m, cudaMemcpyHostToDevice, s));
+        rc = launch_trace(ctx, 0, (const float4*)(dr + off), m, dh + off, nullptr, flags, s);
+        if (rc != PRT_OK) break;
+        PRT_CUDA_TRY(ctx, cudaMemcpyAsync(hits_host + done, dh + off, sizeof(prt_hit) * m, cudaMemcpyDeviceToHost, s));
+        done += m;
+        slot ^= 1;
+    }
+    cudaError_t e0 = cudaStreamSynchronize(ctx->copy_stream[0]);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream[1]);
+    if (rc != PRT_OK) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess) {
+        ctx->set_error("trace_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+        return PRT_ERR_CUDA;
+    }
+    return PRT_OK;
 }
 
 int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev, int32_t* prim_ids_dev,

@@ -5,25 +5,11 @@
 // whose FP32 decisions were within their error bound, in FP64 with the
 // reference's operation order (see traverse.cuh / intersect.cuh).
 #include "context.cuh"
+#include "persist.cuh"
 #include "traverse.cuh"
 
 namespace prt {
 
-template <bool COUNT>
-__device__ __forceinline__ void flush_counters(Counters* ctr, const TraceResult& r, int mode) {
-    if (!COUNT) return;
-    unsigned long long nn = r.n_nodes, nt = r.n_tris, one = 1;
-    for (int o = 16; o > 0; o >>= 1) {
-        nn += __shfl_down_sync(0xffffffffu, nn, o);
-        nt += __shfl_down_sync(0xffffffffu, nt, o);
-        one += __shfl_down_sync(0xffffffffu, one, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&ctr->node_visits, nn);
-        atomicAdd(&ctr->tri_tests, nt);
-        atomicAdd(mode == MODE_ANY ? &ctr->rays_shadow : &ctr->rays_closest, one);
-    }
-}
 
 template <int MODE, bool EXACT, bool COUNT, bool BRUTE>
 __global__ void __launch_bounds__(kTraceThreads)
@@ -37,6 +23,19 @@ trace_kernel(SceneDev sc, const float4* __restrict__ rays, uint64_t n, void* out
     if (active) {
         float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
         trace_one<MODE, EXACT, COUNT, BRUTE>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
+        if (EXACT && MODE == MODE_CLOSEST && !res.uncertain && res.gid >= 0) {
+            // the winner is certain; report its (t,u,v) from the reference's FP64 formula so
+            // that t is the oracle's t rounded to f32 (FP32 watertight t degrades when grazing)
+            const float4* tp = sc.verts_gid + 3ull * res.gid;
+            double o[3] = {(double)ro.x, (double)ro.y, (double)ro.z};
+            double d[3] = {(double)rd.x, (double)rd.y, (double)rd.z};
+            double t, u, v;
+            if (mt_f64(xyz(__ldg(tp)), xyz(__ldg(tp + 1)), xyz(__ldg(tp + 2)), o, d, -1e300, 1e300, t, u, v)) {
+                res.t = (float)t; res.u = (float)u; res.v = (float)v;
+            } else {
+                res.uncertain = true;
+            }
+        }
         if (EXACT && res.uncertain) {
             unsigned int slot = atomicAdd(flag_count, 1u);
             flag_list[slot] = (uint32_t)i;
@@ -68,6 +67,33 @@ trace_kernel(SceneDev sc, const float4* __restrict__ rays, uint64_t n, void* out
             atomicAdd(MODE == MODE_ANY ? &ctr->rays_shadow : &ctr->rays_closest, one);
         }
     }
+}
+
+// Throughput path (plain FP32, BVH): persistent warps with dynamic ray fetch (persist.cuh).
+template <int MODE>
+struct ApiIO {
+    const float4* rays;
+    void* out;
+    __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
+        ro = __ldg(rays + 2ull * k);
+        rd = __ldg(rays + 2ull * k + 1);
+        tag = k;
+    }
+    __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
+        if (MODE == MODE_CLOSEST)
+            reinterpret_cast<float4*>(out)[tag] = make_float4(gid >= 0 ? t : 0.0f, u, v, __int_as_float(gid));
+        else
+            reinterpret_cast<uint8_t*>(out)[tag] = gid >= 0 ? 1 : 0;
+    }
+};
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads)
+trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out,
+                        unsigned int* fetch, Counters* ctr) {
+    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    ApiIO<MODE> io{rays, out};
+    trace_persistent<MODE, COUNT>(sc, io, fetch, n, &s_stack[0][threadIdx.x], ctr);
 }
 
 template <int MODE, bool BRUTE>
@@ -135,6 +161,28 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
         ctx->flag_cap = n;
     }
     if (exact) PRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag_count, 0, sizeof(unsigned int), stream));
+    if (!exact && !brute && mode != MODE_ALL) {
+        // one fetch counter per in-flight launch (host-buffer calls pipeline two streams)
+        unsigned int* fetch = ctx->fetch_counters + (ctx->fetch_next++ % prt_ctx::kFetchRing);
+        PRT_CUDA_TRY(ctx, cudaMemsetAsync(fetch, 0, sizeof(unsigned int), stream));
+        if (ctx->grid_persist == 0) {
+            int b = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_persistent_kernel<MODE_CLOSEST, false>, kTraceThreads, 0);
+            ctx->grid_persist = ctx->num_sms * (b > 0 ? b : 8);
+        }
+        unsigned g = (unsigned)ctx->grid_persist;
+        unsigned need = (unsigned)((n + kTraceThreads - 1) / kTraceThreads);
+        if (need < g) g = need;
+        if (mode == MODE_CLOSEST) {
+            if (count) trace_persistent_kernel<MODE_CLOSEST, true><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
+            else trace_persistent_kernel<MODE_CLOSEST, false><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
+        } else {
+            if (count) trace_persistent_kernel<MODE_ANY, true><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
+            else trace_persistent_kernel<MODE_ANY, false><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
+        }
+        PRT_CUDA_TRY(ctx, cudaGetLastError());
+        return PRT_OK;
+    }
     dim3 grid((unsigned)((n + kTraceThreads - 1) / kTraceThreads));
     switch (mode) {
         case MODE_CLOSEST: launch1<MODE_CLOSEST>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;

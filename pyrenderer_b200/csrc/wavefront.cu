@@ -26,6 +26,7 @@
 // after the first bounce, NEE without 1/pi or pdf, one-sided emitter.
 #include "context.cuh"
 #include "shading.cuh"
+#include "persist.cuh"
 #include "traverse.cuh"
 
 namespace prt {
@@ -123,55 +124,55 @@ __global__ void raygen_kernel(CamDev cam, WaveParams P, float4* rays, float4* be
     queue[pid] = pid;
 }
 
-// persistent closest-hit over the current queue
+// persistent closest-hit over the current queue (persist.cuh: lane-level dynamic fetch)
+struct QueueClosestIO {
+    const float4* rays;
+    float4* hits;
+    const uint32_t* queue;
+    __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
+        tag = queue[k];
+        ro = rays[2 * (size_t)tag];
+        rd = rays[2 * (size_t)tag + 1];
+    }
+    __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
+        hits[tag] = make_float4(t, u, v, __int_as_float(gid));
+    }
+};
+
 __global__ void __launch_bounds__(kTraceThreads)
 closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
                const uint32_t* __restrict__ queue, unsigned int* cnt) {
     __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
-    const unsigned int n = cnt[0];
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(cnt + 3, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned int k = base + lane;
-        if (k < n) {
-            uint32_t pid = queue[k];
-            float4 ro = rays[2 * (size_t)pid], rd = rays[2 * (size_t)pid + 1];
-            TraceResult res;
-            trace_one<MODE_CLOSEST, false, false, false>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
-            hits[pid] = make_float4(res.t, res.u, res.v, __int_as_float(res.gid));
-        }
-        __syncwarp();
-    }
+    QueueClosestIO io{rays, hits, queue};
+    trace_persistent<MODE_CLOSEST, false>(sc, io, cnt + 3, cnt[0], &s_stack[0][threadIdx.x], nullptr);
 }
+
+// shadow rays: an unoccluded ray adds its pending NEE contribution to the path's radiance
+struct QueueShadowIO {
+    const float4* srays;
+    const float4* scontrib;
+    float4* L;
+    __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
+        tag = k;
+        ro = srays[2 * (size_t)k];
+        rd = srays[2 * (size_t)k + 1];
+    }
+    __device__ __forceinline__ void store(uint32_t tag, float, float, float, int gid) const {
+        if (gid < 0) {
+            float4 c = scontrib[tag];
+            uint32_t pid = __float_as_uint(c.w);
+            float4 l = L[pid];
+            L[pid] = make_float4(l.x + c.x, l.y + c.y, l.z + c.z, 0.f);
+        }
+    }
+};
 
 __global__ void __launch_bounds__(kTraceThreads)
 shadow_kernel(SceneDev sc, const float4* __restrict__ srays, const float4* __restrict__ scontrib,
               float4* L, unsigned int* cnt) {
     __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
-    const unsigned int n = cnt[2];
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(cnt + 4, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned int k = base + lane;
-        if (k < n) {
-            float4 ro = srays[2 * (size_t)k], rd = srays[2 * (size_t)k + 1];
-            TraceResult res;
-            trace_one<MODE_ANY, false, false, false>(sc, ro, rd, &s_stack[0][threadIdx.x], res);
-            if (res.gid < 0) {
-                float4 c = scontrib[k];
-                uint32_t pid = __float_as_uint(c.w);
-                float4 l = L[pid];
-                L[pid] = make_float4(l.x + c.x, l.y + c.y, l.z + c.z, 0.f);
-            }
-        }
-        __syncwarp();
-    }
+    QueueShadowIO io{srays, scontrib, L};
+    trace_persistent<MODE_ANY, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
 }
 
 __device__ __forceinline__ float guard_beta(float albedo, float cz, float pdf) {
@@ -219,7 +220,16 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                                              l.z + P.light_color.z * b.z * w, 0.f);
                     }
                 } else {
-                    float3 p = make_float3(fmaf(d.x, h.x, o.x), fmaf(d.y, h.x, o.y), fmaf(d.z, h.x, o.z));
+                    // Hit point.  The reference evaluates o + d*t in f64 (fast_op.py:110-112); in
+                    // FP32 that leaves the point ~1e-7 off the surface and grazing continuation
+                    // rays then re-hit it beyond t_min = 1e-5.  The barycentric form lands on the
+                    // triangle's plane (exactly, for axis-aligned faces) -- same point, real arithmetic.
+                    float3 q0 = xyz(__ldg(sc.verts_gid + 3 * (size_t)gid)),
+                           q1 = xyz(__ldg(sc.verts_gid + 3 * (size_t)gid + 1)),
+                           q2 = xyz(__ldg(sc.verts_gid + 3 * (size_t)gid + 2));
+                    float3 e1 = q1 - q0, e2 = q2 - q0;
+                    float3 p = make_float3(fmaf(h.z, e2.x, fmaf(h.y, e1.x, q0.x)), fmaf(h.z, e2.y, fmaf(h.y, e1.y, q0.y)),
+                                           fmaf(h.z, e2.z, fmaf(h.y, e1.z, q0.z)));
                     bool front = dot(n, nd) >= 0.0f;
                     if (m.two_sided && !front) n = -n;  // mathematics/shapes.py:99-102
                     uint4 r1 = rng4(P.seed, pixel, s, bounce, 1);
@@ -423,7 +433,13 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
         for (uint32_t b = 0; b < p->max_depth; ++b) {
             uint32_t* qin = w->queue[b & 1];
             uint32_t* qout = w->queue[(b & 1) ^ 1];
-            closest_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt);
+            if (b == 0 && (p->flags & PRT_RENDER_EXACT_PRIMARY)) {
+                // bounce 0: queue == identity, rays contiguous -> the API-level exact trace applies
+                rc = launch_trace(ctx, MODE_CLOSEST, w->rays, n_paths, w->hits, nullptr, PRT_TRACE_EXACT, stream);
+                if (rc != PRT_OK) return rc;
+            } else {
+                closest_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt);
+            }
             shade_kernel<<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
                                                             w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
             shadow_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->srays, w->scontrib, w->L, w->cnt);

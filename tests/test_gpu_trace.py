@@ -1,0 +1,272 @@
+"""GPU parity tests for the intersection / BVH path, through the C ABI.
+
+Contract (BASELINE.json north_star): triangle ids bit-exact against the
+reference's intersection code (here: the oracle, itself bit-exact against the
+reference's numba kernel -- tests/test_oracle_golden.py); t within 4 ulp(f32).
+PRT_TRACE_EXACT is the parity mode: FP32 watertight traversal + FP64 replay of
+the flagged low-margin rays.  The plain FP32 mode is also measured and must
+disagree on at most a tiny, reported fraction of rays.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import CUBE_OBJ, make_rays, random_rays, random_soup
+
+pytestmark = pytest.mark.gpu
+
+F32MAX = 3.4028234663852886e+38
+EXACT, COUNT, BRUTE = 1, 2, 4
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def gpu_closest(ctx, rays, flags):
+    torch = _torch()
+    r = torch.from_numpy(np.ascontiguousarray(rays, np.float32)).cuda()
+    h = torch.empty((rays.shape[0], 4), dtype=torch.float32, device="cuda")
+    ctx.trace_closest(r, rays.shape[0], h, flags)
+    torch.cuda.synchronize()
+    h = h.cpu().numpy()
+    return h[:, 3].copy().view(np.int32), h[:, 0].astype(np.float64), h[:, 1], h[:, 2]
+
+
+def check_against_oracle(ctx, tris, rays, flags, label, ref=None):
+    ids_o, t_o, u_o, v_o = ref if ref is not None else oracle.closest_hit(tris, rays)
+    ctx.reset_counters()
+    ids_g, t_g, u_g, v_g = gpu_closest(ctx, rays, flags)
+    bad = np.nonzero(ids_g != ids_o)[0]
+    assert bad.size == 0, f"{label}: {bad.size} id mismatches, first {bad[:5]} gpu {ids_g[bad[:5]]} ref {ids_o[bad[:5]]}"
+    hit = ids_o >= 0
+    rel = np.abs(t_g[hit] - t_o[hit]) / np.maximum(np.abs(t_o[hit]), 1e-30)
+    assert rel.max() <= 4 * 2.0 ** -23, f"{label}: t off by {rel.max() / 2.0 ** -23:.2f} ulp"
+    assert np.abs(u_g[hit] - u_o[hit]).max() < 1e-3 and np.abs(v_g[hit] - v_o[hit]).max() < 1e-3
+    c = ctx.counters()
+    print(f"[{label}] rays {rays.shape[0]} hits {hit.sum()} flagged(FP64 replay) {c['flagged_rays']}")
+    return c["flagged_rays"]
+
+
+def test_abi_roundtrip_and_errors(gpu_ctx):
+    from pyrenderer_b200 import _abi
+    ctx = _abi.Context(0)
+    rays = random_rays(64)
+    torch = _torch()
+    r = torch.from_numpy(rays).cuda()
+    h = torch.empty((64, 4), dtype=torch.float32, device="cuda")
+    with pytest.raises(_abi.PrtError) as e:  # trace before a scene exists
+        ctx.trace_closest(r, 64, h, 0)
+    assert "[-3]" in str(e.value) and "scene" in str(e.value)
+    ctx.set_triangles(random_soup(10))
+    with pytest.raises(_abi.PrtError) as e:  # BVH traversal before the build
+        ctx.trace_closest(r, 64, h, 0)
+    assert "BVH not built" in str(e.value)
+    ctx.trace_closest(r, 64, h, BRUTE)  # brute force needs no BVH
+    with pytest.raises(_abi.PrtError):
+        ctx.set_triangles(random_soup(4), light_tris=[9])  # light id out of range
+    with pytest.raises(_abi.PrtError):
+        ctx.build_bvh(max_leaf_tris=9)
+    ctx.close()
+    with pytest.raises(_abi.PrtError):
+        _abi.Context(99)
+
+
+@pytest.mark.parametrize("case", ["cornell", "soup64"])
+def test_golden_rays(gpu_ctx, golden, case):
+    """The rays the REFERENCE's numba kernel was run on (make_golden.py)."""
+    tris = golden[f"ch_{case}_tris"]
+    rays = make_rays(golden[f"ch_{case}_o"], golden[f"ch_{case}_d"], tmin=1.1754943508222875e-38, tmax=F32MAX)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh()
+    for flags, label in ((EXACT | BRUTE, "brute"), (EXACT, "bvh")):
+        ids_g, t_g, _, _ = gpu_closest(gpu_ctx, rays, flags)
+        assert np.array_equal(ids_g, golden[f"ch_{case}_ids"]), label
+        hit = ids_g >= 0
+        rel = np.abs(t_g[hit] - golden[f"ch_{case}_t"][hit]) / golden[f"ch_{case}_t"][hit]
+        assert rel.max() <= 4 * 2.0 ** -23
+
+
+def test_cornell_primary_ids_1024(gpu_ctx, cornell):
+    """Every primary ray of the 1024x1024 Cornell camera (pixel centres): device ray
+    generation bit-equal to the oracle camera, ids bit-exact in EXACT mode."""
+    torch = _torch()
+    scene, cam = cornell
+    a = scene.arrays()
+    gpu_ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])
+    st = gpu_ctx.build_bvh()
+    assert st["n_tris"] == 36
+    iview, sw, sh, focal, W, H = cam.device_record()
+    gpu_ctx.set_camera(iview, sw, sh, focal, W, H)
+    rays_d = torch.empty((H * W, 8), dtype=torch.float32, device="cuda")
+    gpu_ctx.generate_rays(rays_d, seed=0, s0=0, s1=1, jitter=False, tmin=1e-5, tmax=99999.9)
+    torch.cuda.synchronize()
+    rays = rays_d.cpu().numpy()
+    ocam = oracle.make_camera(iview, sw, sh, focal, W, H)
+    rays_o = oracle.generate_rays(ocam, jitter=False).reshape(-1, 8)
+    assert np.array_equal(rays.view(np.uint32), rays_o.view(np.uint32)), "device raygen != oracle camera"
+    ref = oracle.closest_hit(a["tris"], rays)
+    flagged = check_against_oracle(gpu_ctx, a["tris"], rays, EXACT, "cornell-1024-bvh", ref)
+    check_against_oracle(gpu_ctx, a["tris"], rays, EXACT | BRUTE, "cornell-1024-brute", ref)
+    assert flagged < 0.01 * rays.shape[0]
+    # plain FP32 mode: report, and bound, the disagreement
+    ids_o = ref[0]
+    ids_f, _, _, _ = gpu_closest(gpu_ctx, rays, 0)
+    frac = np.mean(ids_f != ids_o)
+    print(f"[cornell-1024] FP32-only id mismatch fraction {frac:.2e}")
+    assert frac < 1e-3
+
+
+def test_cube_obj_primary_ids_1024(gpu_ctx):
+    """BASELINE config 2: media/cube.obj, 1024x1024 primary rays, camera of SURVEY 8d."""
+    from pyrenderer_b200.core.camera import Camera
+    from pyrenderer_b200.io_utils.read_tungsten import read_obj
+    torch = _torch()
+    v, f = read_obj(CUBE_OBJ)
+    tris = v[f].astype(np.float32)
+    cam = Camera([2.6, 2.1, 3.4], [0.5, 0.5, 0.5], [0, 1, 0], [1024, 1024], fov=35.0)
+    iview, sw, sh, focal, W, H = cam.device_record()
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh()
+    gpu_ctx.set_camera(iview, sw, sh, focal, W, H)
+    rays_d = torch.empty((H * W, 8), dtype=torch.float32, device="cuda")
+    gpu_ctx.generate_rays(rays_d, jitter=False, tmin=1e-5, tmax=F32MAX)
+    torch.cuda.synchronize()
+    rays = rays_d.cpu().numpy()
+    ocam = oracle.make_camera(iview, sw, sh, focal, W, H)
+    assert np.array_equal(rays.view(np.uint32),
+                          oracle.generate_rays(ocam, jitter=False, tmax=F32MAX).reshape(-1, 8).view(np.uint32))
+    check_against_oracle(gpu_ctx, tris, rays, EXACT, "cube-1024-bvh")
+    ids, _, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+    assert 0.05 < np.mean(ids >= 0) < 0.9 and set(np.unique(ids)) <= set(range(-1, 12))
+
+
+@pytest.mark.parametrize("nt,nr,leaf", [(1, 2000, 4), (2, 2000, 4), (37, 20000, 1), (5000, 100000, 4), (20000, 100000, 7)])
+def test_random_soup_bvh_vs_oracle(gpu_ctx, nt, nr, leaf):
+    tris = random_soup(nt, seed=nt)
+    if nt <= 2:
+        tris *= 0.0
+        tris += random_soup(nt, seed=5) * 0.5 + 0.25  # big triangles so that rays hit
+    rays = random_rays(nr, seed=nt + 1)
+    gpu_ctx.set_triangles(tris)
+    st = gpu_ctx.build_bvh(max_leaf_tris=leaf)
+    assert st["n_tris"] == nt and st["depth"] < 90
+    ref = oracle.closest_hit(tris, rays)
+    check_against_oracle(gpu_ctx, tris, rays, EXACT, f"soup{nt}-bvh", ref)
+    check_against_oracle(gpu_ctx, tris, rays, EXACT | BRUTE, f"soup{nt}-brute", ref)
+    ids_o = ref[0]
+    ids_f, _, _, _ = gpu_closest(gpu_ctx, rays, 0)
+    frac = np.mean(ids_f != ids_o)
+    print(f"[soup{nt}] FP32-only id mismatch fraction {frac:.2e}")
+    assert frac < 1e-3
+
+
+def test_rotations_and_leaf_sizes_do_not_change_hits(gpu_ctx):
+    tris = random_soup(30000, seed=3)
+    rays = random_rays(100000, seed=4)
+    ref = None
+    for leaf, rot in ((1, 0), (1, 1), (4, 1), (7, 0)):
+        gpu_ctx.set_triangles(tris)
+        gpu_ctx.build_bvh(max_leaf_tris=leaf, rotations=rot)
+        ids, t, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+        if ref is None:
+            ref = (ids, t)
+        assert np.array_equal(ids, ref[0]) and np.array_equal(t, ref[1])
+
+
+def test_any_and_all_hits(gpu_ctx):
+    torch = _torch()
+    tris = random_soup(3000, seed=9)
+    rays = random_rays(50000, seed=10, tmax=0.35)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh()
+    r = torch.from_numpy(rays).cuda()
+    occ = torch.empty(rays.shape[0], dtype=torch.uint8, device="cuda")
+    cnt = torch.empty(rays.shape[0], dtype=torch.int32, device="cuda")
+    sums = torch.empty(rays.shape[0], dtype=torch.int64, device="cuda")
+    occ_o = oracle.any_hit(tris, rays)
+    cnt_o, sums_o = oracle.all_hits(tris, rays)
+    assert 0.2 < occ_o.mean() < 0.98 and cnt_o.max() >= 3
+    for flags in (EXACT, EXACT | BRUTE):
+        gpu_ctx.trace_any(r, rays.shape[0], occ, flags)
+        gpu_ctx.trace_all(r, rays.shape[0], cnt, sums, flags)
+        torch.cuda.synchronize()
+        assert np.array_equal(occ.cpu().numpy(), occ_o)
+        assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o)  # the full hit SET per ray
+        assert np.array_equal(sums.cpu().numpy().view(np.uint64), sums_o)
+
+
+def test_edge_cases(gpu_ctx, cornell):
+    torch = _torch()
+    # empty scene
+    gpu_ctx.set_triangles(np.zeros((0, 3, 3), np.float32))
+    gpu_ctx.build_bvh()
+    ids, _, _, _ = gpu_closest(gpu_ctx, random_rays(100), EXACT)
+    assert np.all(ids == -1)
+    ids, _, _, _ = gpu_closest(gpu_ctx, random_rays(100), BRUTE)
+    assert np.all(ids == -1)
+    # zero rays
+    gpu_ctx.trace_closest(torch.empty((0, 8), device="cuda"), 0, torch.empty((0, 4), device="cuda"), 0)
+    # degenerate (zero-area, duplicated) triangles mixed into a soup + coincident centroids
+    tris = random_soup(500, seed=21)
+    tris[10] = tris[10, 0]  # point
+    tris[11, 2] = tris[11, 1]  # segment
+    tris[20:40] = tris[20]  # 20 identical triangles: identical Morton codes AND exact t ties
+    rays = random_rays(30000, seed=22)
+    # aim a few thousand rays exactly at the duplicated triangle
+    c = tris[20].mean(axis=0)
+    d = c[None] - rays[:3000, 0:3]
+    rays[:3000, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh(max_leaf_tris=2)
+    check_against_oracle(gpu_ctx, tris, rays, EXACT, "degenerate")
+    ids, _, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+    assert np.sum(ids == 20) > 100 and not np.any((ids > 20) & (ids < 40))  # lowest id wins ties
+    # Cornell: axis-aligned rays, rays through shared edges / vertices, origins on surfaces
+    scene, _ = cornell
+    a = scene.arrays()
+    gpu_ctx.set_triangles(a["tris"])
+    gpu_ctx.build_bvh()
+    o, d = [], []
+    for x in np.linspace(-0.9, 0.9, 37):
+        for y in np.linspace(0.1, 1.9, 37):
+            o.append([x, y, 0.9]); d.append([0, 0, -1])       # axis aligned, hits back wall / boxes
+            o.append([x, 0.0, y - 1.0]); d.append([0, 1, 0])  # origin ON the floor
+            o.append([0.0, 1.0, 0.5]); d.append([x, y - 1.0, -0.5])  # through the wall diagonals
+    o = np.array(o, np.float32); d = np.array(d, np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = make_rays(o, d.astype(np.float32), tmin=1e-5, tmax=99999.9)
+    check_against_oracle(gpu_ctx, a["tris"], rays, EXACT, "cornell-edges")
+    check_against_oracle(gpu_ctx, a["tris"], rays, EXACT | BRUTE, "cornell-edges-brute")
+
+
+def test_host_buffer_entry_point(gpu_ctx):
+    tris = random_soup(2000, seed=31)
+    rays = random_rays(20000, seed=32)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh()
+    h = gpu_ctx.trace_closest_host(rays, EXACT)
+    ids_o, _, _, _ = oracle.closest_hit(tris, rays)
+    assert np.array_equal(h["tri"], ids_o)
+
+
+def test_million_triangle_soup_bvh_equals_exhaustive(gpu_ctx):
+    """BASELINE config 4 size (1M triangles): the BVH answer equals the exhaustive GPU
+    answer for every ray (size-independent property), and a CPU-oracle spot check."""
+    tris = random_soup(1_000_000, seed=7)
+    rays = random_rays(1 << 17, seed=11)
+    gpu_ctx.set_triangles(tris)
+    st = gpu_ctx.build_bvh()
+    print("[soup1M] bvh", st)
+    assert st["n_tris"] == 1_000_000 and 0 < st["n_nodes"] < 1_000_000
+    ids_b, t_b, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+    ids_x, t_x, _, _ = gpu_closest(gpu_ctx, rays[: 1 << 14], EXACT | BRUTE)
+    assert np.array_equal(ids_b[: 1 << 14], ids_x) and np.array_equal(t_b[: 1 << 14], t_x)
+    ids_o, t_o, _, _ = oracle.closest_hit(tris, rays[:256])
+    assert np.array_equal(ids_b[:256], ids_o)
+    assert np.mean(ids_b >= 0) > 0.8
+    gpu_ctx.reset_counters()
+    gpu_closest(gpu_ctx, rays, COUNT)
+    c = gpu_ctx.counters()
+    print(f"[soup1M] mean node visits {c['node_visits'] / rays.shape[0]:.1f} tri tests {c['tri_tests'] / rays.shape[0]:.1f}")
