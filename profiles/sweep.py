@@ -1,0 +1,53 @@
+"""Tuning sweep on soup-1M: BVH options and persistent-traversal knobs -> Mrays/s, N_node, N_tri.
+usage: python profiles/sweep.py bvh | knobs"""
+import os, subprocess, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import soup
+N = 1 << 22
+
+def rays(dev):
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    r = torch.empty((N, 8), dtype=torch.float32, device=dev)
+    r[:, 0:3] = torch.rand((N, 3), generator=g, device=dev)
+    d = torch.randn((N, 3), generator=g, device=dev)
+    r[:, 4:7] = d / d.norm(dim=1, keepdim=True)
+    r[:, 3] = 1e-5; r[:, 7] = 3.4e38
+    return r
+
+def measure(ctx, r, hits, reps=3):
+    from pyrenderer_b200 import _abi
+    ctx.reset_counters(); ctx.trace_closest(r, N, hits, _abi.TRACE_COUNT); c = ctx.counters()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ctx.trace_closest(r, N, hits, 0); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return N / best / 1e3, c["node_visits"] / N, c["tri_tests"] / N
+
+def main():
+    from pyrenderer_b200 import _abi
+    dev = torch.device("cuda", 0)
+    tris = torch.from_numpy(soup(1_000_000)).to(dev)
+    r = rays(dev); hits = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    mode = sys.argv[1] if len(sys.argv) > 1 else "bvh"
+    if mode == "bvh":
+        ctx = _abi.Context(0)
+        for leaf in (1, 2, 4, 7):
+            for cn, ct in ((1.0, 1.0), (1.0, 0.5), (1.0, 2.0)):
+                for rot in (0, 1):
+                    ctx.set_triangles_dev(tris, 1_000_000)
+                    st = ctx.build_bvh(max_leaf_tris=leaf, cost_node=cn, cost_tri=ct, rotations=rot)
+                    m, nn, nt = measure(ctx, r, hits)
+                    print(f"leaf {leaf} cn {cn} ct {ct} rot {rot}: {m:8.1f} Mrays/s  N_node {nn:6.1f} N_tri {nt:5.1f} nodes {st['n_nodes']} depth {st['depth']} sah {st['sah_cost']:.1f} build {st['ms_total']:.2f} ms", flush=True)
+    else:
+        for ri in (2, 4, 6, 8, 12, 16):
+            for lb in (1, 4, 6, 8, 12, 16):
+                os.environ["PRT_REFILL_IDLE"] = str(ri); os.environ["PRT_LEAF_BATCH"] = str(lb)
+                ctx = _abi.Context(0)
+                ctx.set_triangles_dev(tris, 1_000_000); ctx.build_bvh()
+                m, nn, nt = measure(ctx, r, hits)
+                print(f"refill_idle {ri:2d} leaf_batch {lb:2d}: {m:8.1f} Mrays/s", flush=True)
+                ctx.close()
+
+main()

@@ -39,6 +39,7 @@ struct prt_ctx {
     unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
     unsigned fetch_next = 0;
     int grid_persist = 0;
+    int refill_idle = 6, leaf_batch = 6;
 
     // device staging of the *_host entry points (grow-only, reused across calls)
     void* stage[2] = {nullptr, nullptr};
@@ -66,6 +67,7 @@ struct prt_ctx {
         s.light_tris = light_tris;
         s.verts_gid = verts_gid;
         s.nt = nt; s.n_nodes = n_nodes; s.nl = nl; s.nm = nm;
+        s.refill_idle = refill_idle; s.leaf_batch = leaf_batch;
         return s;
     }
 };

@@ -1,48 +1,78 @@
-// persist.cuh -- persistent-warp FP32 traversal with lane-level dynamic ray fetch.
+// persist.cuh -- persistent-warp FP32 traversal with lane-level dynamic ray fetch
+// and deferred leaves.
 //
-// Incoherent rays have very different traversal lengths (soup-1M: mean 83 node
-// visits, long tail).  With one ray per thread a warp runs until its LONGEST ray
-// ends; ncu measured 6.7 of 32 lanes active (profiles/r1_trace_kernel_ncu.txt).
-// Here warps are persistent: whenever fewer than `kRefillBelow` lanes still hold a
-// ray, the idle lanes pull new rays from a global counter (one atomic per warp,
-// ballot + prefix popcount for the slot), after Aila & Laine, "Understanding the
-// efficiency of ray traversal on GPUs" (HPG 2009).  Inside, the loop is
-// while-while: every lane walks internal records until it reaches a leaf, then the
-// warp intersects leaves together.
+// Incoherent rays have very different traversal lengths (soup-1M: mean 83 record
+// visits, ~3 leaf visits, long tail).  With one ray per thread a warp runs until its
+// LONGEST ray ends and every leaf visit stalls the 31 other lanes: ncu measured 6.7
+// of 32 lanes active (profiles/r1_trace_kernel_ncu.txt).  Here
+//   * warps are persistent: when `refill_idle` or more lanes hold no ray, the idle
+//     lanes pull new rays from a global counter (one atomic per warp, ballot +
+//     prefix popcount for the slot) -- Aila & Laine, "Understanding the efficiency
+//     of ray traversal on GPUs" (HPG 2009);
+//   * every loop iteration is ONE record visit for the lanes that are at an internal
+//     record; a lane that reaches a leaf parks until `leaf_batch` lanes are parked
+//     (or nobody has records left), then the parked lanes intersect their leaves
+//     together.  Record visits are >90 % of the instructions, so they are what is
+//     kept convergent.
 //
-// IO is a functor: load(k, ro, rd, tag) / store(tag, t, u, v, gid); it is what
-// binds this loop to the API ray arrays or to the wavefront queues.
+// IO is a functor: load(k, ro, rd, tag) / store(tag, t, u, v, gid); it binds this
+// loop to the API ray arrays or to the wavefront queues.
 #pragma once
 #include "bvh.cuh"
 #include "traverse.cuh"
 
 namespace prt {
 
-constexpr int kRefillBelow = 22;
-constexpr uint32_t kDone = 0xFFFFFFFFu;  // has kLeafFlag set: ends the node phase
+// scheduling knobs live in SceneDev (refill_idle: refill when at least this many lanes are idle;
+// leaf_batch: intersect leaves when at least this many lanes are parked); defaults in context.cuh,
+// overridable with PRT_REFILL_IDLE / PRT_LEAF_BATCH for tuning sweeps.
+constexpr uint32_t kDone = 0xFFFFFFFFu;  // has kLeafFlag set
 
-__device__ __forceinline__ void sstack_push(uint32_t saddr, uint32_t* ovf, int& sp, uint32_t v) {
-    if (sp < kSmemStack) asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 4u)), "r"(v) : "memory");
-    else ovf[sp - kSmemStack] = v;
+// Per-lane stack of (child reference, entry distance) pairs: kPStack levels in shared
+// memory ([level][lane] of 8-byte slots, conflict-free), deeper levels in local memory.
+// Keeping the entry distance lets a pop discard, without touching memory, every
+// subtree that a closer hit found in the meantime has made irrelevant.
+constexpr int kPStack = 16;
+constexpr int kPStackOvf = kMaxStack - kPStack;
+
+__device__ __forceinline__ void sstack_push(uint32_t saddr, uint2* ovf, int& sp, uint32_t ref, float t) {
+    if (sp < kPStack)
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)), "r"(ref), "r"(__float_as_uint(t)) : "memory");
+    else
+        ovf[sp - kPStack] = make_uint2(ref, __float_as_uint(t));
     ++sp;
 }
-__device__ __forceinline__ uint32_t sstack_pop(uint32_t saddr, const uint32_t* ovf, int& sp) {
+__device__ __forceinline__ uint32_t sstack_pop(uint32_t saddr, const uint2* ovf, int& sp, float& t) {
     --sp;
-    uint32_t v;
-    if (sp < kSmemStack) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + (uint32_t)sp * (kTraceThreads * 4u)) : "memory");
-    else v = ovf[sp - kSmemStack];
-    return v;
+    uint32_t ref, tb;
+    if (sp < kPStack) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)) : "memory");
+    } else {
+        uint2 e = ovf[sp - kPStack];
+        ref = e.x; tb = e.y;
+    }
+    t = __uint_as_float(tb);
+    return ref;
+}
+// pop until an entry that can still beat `bound` (or the stack is empty -> kDone)
+__device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, const uint2* ovf, int& sp, float bound) {
+    while (sp > 0) {
+        float t;
+        const uint32_t ref = sstack_pop(saddr, ovf, sp, t);
+        if (t <= bound) return ref;
+    }
+    return 0xFFFFFFFFu;
 }
 
 template <int MODE, bool COUNT, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsigned int* fetch,
-                                                 unsigned int n, uint32_t* stack_col, Counters* ctr) {
+                                                 unsigned int n, uint2* stack_col, Counters* ctr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
-    uint32_t ovf[kMaxStack - kSmemStack];
-    bool has_ray = false, exhausted = (sc.n_nodes == 0);
+    uint2 ovf[kPStackOvf];
+    bool has_ray = false, exhausted = false;
     // per-ray state
     RayW rw;
     RayBox rb;
@@ -61,18 +91,19 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
     }
 
     while (true) {
-        unsigned idle = __ballot_sync(FULL, !has_ray);
-        if (idle && !exhausted) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !has_ray);
+        if (!exhausted && (__popc(idle) >= sc.refill_idle)) {
             unsigned base = 0;
             const int leader = __ffs(idle) - 1, nidle = __popc(idle);
             if (lane == leader) base = atomicAdd(fetch, (unsigned)nidle);
             base = __shfl_sync(FULL, base, leader);
             if (!has_ray) {
-                unsigned k = base + __popc(idle & lt);
+                const unsigned k = base + __popc(idle & lt);
                 if (k < n) {
                     float4 ro, rd;
                     io.load(k, ro, rd, tag);
-                    float3 o = xyz(ro), d = xyz(rd);
+                    const float3 o = xyz(ro), d = xyz(rd);
                     rw = make_rayw(o, d);
                     rb = make_raybox(o, d);
                     tmin = ro.w; tmax = rd.w;
@@ -84,63 +115,64 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
             }
             if (base + (unsigned)nidle >= n) exhausted = true;
         }
-        if (__ballot_sync(FULL, has_ray) == 0) break;
-        const int thresh = exhausted ? 1 : kRefillBelow;
+        if (exhausted && __ballot_sync(FULL, has_ray) == 0) break;  // (idle mask may be stale after a refill)
 
-        while (true) {
-            if (has_ray) {
-                // ---- node phase: walk internal records until a leaf (or the end)
-                while (!(cur & kLeafFlag)) {
-                    const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
-                    if (COUNT) ++c_nodes;
-                    float t0, t1;
-                    const int m = node_test<false>(n0, n1, rb, tmin, MODE == MODE_CLOSEST ? bt : tmax, t0, t1);
-                    // child references, branch-free (layout: bvh.cuh header)
-                    const uint32_t em = __float_as_uint(n0.w), link = __float_as_uint(n1.w);
-                    const uint32_t c0 = (em >> 24) & 0xFu, c1 = em >> 28;
-                    const uint32_t leaf0 = kLeafFlag | (link << 3) | c0;
-                    const uint32_t leaf1 = kLeafFlag | ((link + c0) << 3) | c1;  // c0 == 0 when child0 is internal
-                    const uint32_t r0 = c0 ? leaf0 : cur + 1;
-                    const uint32_t r1 = c1 ? leaf1 : (c0 ? cur + 1 : link);
-                    if (m == 3) {
-                        const bool swap = MODE == MODE_CLOSEST && t1 < t0;
-                        sstack_push(saddr, ovf, sp, swap ? r0 : r1);
-                        cur = swap ? r1 : r0;
-                    } else if (m) {
-                        cur = (m & 1) ? r0 : r1;
-                    } else {
-                        cur = sp ? sstack_pop(saddr, ovf, sp) : kDone;
-                    }
-                }
-                // ---- leaf phase
-                if (cur != kDone) {
-                    const uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
-                    bool stop = false;
-                    for (uint32_t k = 0; k < cnt; ++k) {
-                        const float4* tp = sc.tris + 3ull * (start + k);
-                        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                        if (COUNT) ++c_tris;
-                        TriHit h;
-                        bool unc;
-                        if (tri_watertight<false>(rw, xyz(a), xyz(b), xyz(c), tmin, MODE == MODE_CLOSEST ? bt : tmax, 0.f, h, unc)) {
-                            const int gid = __float_as_int(a.w);
-                            if (MODE == MODE_CLOSEST) {
-                                if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; }
-                            } else {
-                                bt = h.t; bgid = gid; stop = true;
-                                break;
-                            }
+        // ---- one record visit for every lane that is at an internal record
+        if (has_ray && !(cur & kLeafFlag)) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+            if (COUNT) ++c_nodes;
+            float t0, t1;
+            const int m = node_test<false>(n0, n1, rb, tmin, MODE == MODE_CLOSEST ? bt : tmax, t0, t1);
+            // child references, branch-free (layout: bvh.cuh header)
+            const uint32_t em = __float_as_uint(n0.w), link = __float_as_uint(n1.w);
+            const uint32_t c0 = (em >> 24) & 0xFu, c1 = em >> 28;
+            const uint32_t leaf0 = kLeafFlag | (link << 3) | c0;
+            const uint32_t leaf1 = kLeafFlag | ((link + c0) << 3) | c1;  // c0 == 0 when child0 is internal
+            const uint32_t r0 = c0 ? leaf0 : cur + 1;
+            const uint32_t r1 = c1 ? leaf1 : (c0 ? cur + 1 : link);
+            if (m == 3) {
+                const bool swap = MODE == MODE_CLOSEST && t1 < t0;
+                sstack_push(saddr, ovf, sp, swap ? r0 : r1, swap ? t0 : t1);
+                cur = swap ? r1 : r0;
+            } else if (m) {
+                cur = (m & 1) ? r0 : r1;
+            } else {
+                cur = sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? bt : tmax);
+            }
+        }
+
+        // ---- leaves: parked lanes go together
+        const bool at_leaf = has_ray && (cur & kLeafFlag) && cur != kDone;
+        const unsigned leafm = __ballot_sync(FULL, at_leaf);
+        // idle lanes keep cur == kDone, so "no leaf flag" == "still walking records"
+        const unsigned nodem = ~__ballot_sync(FULL, (cur & kLeafFlag) != 0u);
+        if (leafm && (__popc(leafm) >= sc.leaf_batch || nodem == 0)) {
+            if (at_leaf) {
+                const uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
+                bool stop = false;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const float4* tp = sc.tris + 3ull * (start + k);
+                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    if (COUNT) ++c_tris;
+                    TriHit h;
+                    bool unc;
+                    if (tri_watertight<false>(rw, xyz(a), xyz(b), xyz(c), tmin, MODE == MODE_CLOSEST ? bt : tmax, 0.f, h, unc)) {
+                        const int gid = __float_as_int(a.w);
+                        if (MODE == MODE_CLOSEST) {
+                            if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; }
+                        } else {
+                            bt = h.t; bgid = gid; stop = true;
+                            break;
                         }
                     }
-                    cur = (!stop && sp) ? sstack_pop(saddr, ovf, sp) : kDone;
                 }
-                if (cur == kDone) {
-                    io.store(tag, bt, bu, bv, bgid);
-                    has_ray = false;
-                }
+                cur = stop ? kDone : sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? bt : tmax);
             }
-            if (__popc(__ballot_sync(FULL, has_ray)) < thresh) break;
+        }
+        if (has_ray && cur == kDone) {
+            io.store(tag, bt, bu, bv, bgid);
+            has_ray = false;
         }
     }
     if (COUNT) {

@@ -1,4 +1,5 @@
 // prt_api.cu -- extern "C" entry points declared in include/prt.h.
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -107,6 +108,8 @@ int prt_create(int device, prt_ctx** out) {
     prt_ctx* c = new (std::nothrow) prt_ctx();
     if (!c) return PRT_ERR_NOMEM;
     c->device = device;
+    if (const char* v = getenv("PRT_REFILL_IDLE")) c->refill_idle = atoi(v) > 0 ? atoi(v) : c->refill_idle;
+    if (const char* v = getenv("PRT_LEAF_BATCH")) c->leaf_batch = atoi(v) > 0 ? atoi(v) : c->leaf_batch;
     e = cudaSetDevice(device);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);

@@ -91,7 +91,7 @@ template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads)
 trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out,
                         unsigned int* fetch, Counters* ctr) {
-    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    __shared__ uint2 s_stack[kPStack][kTraceThreads];
     ApiIO<MODE> io{rays, out};
     trace_persistent<MODE, COUNT>(sc, io, fetch, n, &s_stack[0][threadIdx.x], ctr);
 }

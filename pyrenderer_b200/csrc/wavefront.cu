@@ -142,7 +142,7 @@ struct QueueClosestIO {
 __global__ void __launch_bounds__(kTraceThreads)
 closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
                const uint32_t* __restrict__ queue, unsigned int* cnt) {
-    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    __shared__ uint2 s_stack[kPStack][kTraceThreads];
     QueueClosestIO io{rays, hits, queue};
     trace_persistent<MODE_CLOSEST, false>(sc, io, cnt + 3, cnt[0], &s_stack[0][threadIdx.x], nullptr);
 }
@@ -170,7 +170,7 @@ struct QueueShadowIO {
 __global__ void __launch_bounds__(kTraceThreads)
 shadow_kernel(SceneDev sc, const float4* __restrict__ srays, const float4* __restrict__ scontrib,
               float4* L, unsigned int* cnt) {
-    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    __shared__ uint2 s_stack[kPStack][kTraceThreads];
     QueueShadowIO io{srays, scontrib, L};
     trace_persistent<MODE_ANY, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
 }
