@@ -66,46 +66,69 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks + throttle reasons, sampled every 100 ms from `start()` on; `summary()`
+    keeps the samples taken between `mark_begin()` and `mark_end()` (the timed region); if the
+    region was shorter than one sampling period it falls back to the samples since start()
+    (warm-up + timed region, all under load)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
+
+            def pump():
+                for line in self.proc.stdout:
+                    self.rows.append((time.time(), line))
+            self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
+            time.sleep(0.5)  # let nvidia-smi come up before the GPU work starts
         except Exception:
             self.proc = None
         return self
 
-    def __exit__(self, *a):
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
+            time.sleep(0.15)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, line in rows:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e18) + 0.1]
+        scope = "timed region"
+        sm, mx, reasons = parse(inside)
+        if not sm:
+            sm, mx, reasons = parse(self.rows)
+            scope = "warm-up + timed region"
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "scope": scope}
 
 
 def run_reference(args):
@@ -141,7 +164,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--render-spp", type=int, default=16, help="Cornell samples per pixel per step per GPU")
@@ -211,16 +234,19 @@ def main():
     bytes_per_ray = 48.0 + 32.0 * n_node + 48.0 * n_tri
     hit_frac = float((hits[:, 3].view(torch.int32) >= 0).float().mean().item())
 
+    clk = ClockSampler(local).start()
     for s in range(args.warmup):
         ctx.trace_closest(batches[s % N_BATCHES], RAYS_PER_BATCH, hits, 0)
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as clk:
-        ev[0].record()
-        for s in range(args.steps):
-            ctx.trace_closest(batches[(args.warmup + s) % N_BATCHES], RAYS_PER_BATCH, hits, 0)
-            ev[s + 1].record()
-        barrier()
+    clk.mark_begin()
+    ev[0].record()
+    for s in range(args.steps):
+        ctx.trace_closest(batches[(args.warmup + s) % N_BATCHES], RAYS_PER_BATCH, hits, 0)
+        ev[s + 1].record()
+    barrier()
+    clk.mark_end()
+    clk.stop()
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     kern_ms = float(np.mean([ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]))
     ms_per_step = total_ms / args.steps
@@ -283,10 +309,13 @@ def main():
         if world > 1:
             dist.all_reduce(t)
         # e2e: host accumulation buffer through prt_render_host (upload + render + download)
-        host_acc = np.zeros((H, W, 4), np.float32)
+        host_acc = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory().numpy()
+        rctx.render_host(rctx.render_params(seed=1, spp_begin=0, spp_end=1, max_depth=depth), host_acc)  # warm
+        barrier()
         t0 = time.perf_counter()
-        rctx.render_host(rctx.render_params(seed=1, spp_begin=0, spp_end=spp, max_depth=depth), host_acc)
-        r_e2e_ms = (time.perf_counter() - t0) * 1e3
+        for k in range(2):
+            rctx.render_host(rctx.render_params(seed=1, spp_begin=k * spp, spp_end=(k + 1) * spp, max_depth=depth), host_acc)
+        r_e2e_ms = (time.perf_counter() - t0) * 1e3 / 2
         waves = (spp * W * H + (4 << 20) - 1) // (4 << 20)
         launches_render = waves * (2 + 4 * depth)
         render = {"workload": f"cornell-box {W}x{H}, max depth {depth}, {spp} spp/step/GPU, sample-sharded"
@@ -330,8 +359,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": RAYS_PER_BATCH * 32,
                     "d2h_bytes_per_step": RAYS_PER_BATCH * 16, "ms_per_step": e2e_ms,
                     "api": "prt_trace_closest_host (pinned host rays -> host hits)"},
-            "gpu_launches": args.steps * 1 + (args.steps * launches_render),
-            "roofline": {"bound": "hbm", "kernel": "prt::trace_kernel<CLOSEST> (traverse.cu)", "achieved": achieved,
+            "gpu_launches": args.steps * 1,  # timed region of `value`: one trace_persistent_kernel per step (render leg: see render.gpu_launches_per_step)
+            "roofline": {"bound": "hbm", "kernel": "prt::trace_persistent_kernel<CLOSEST> (traverse.cu / persist.cuh)", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
                          "kernel_ms": kern_ms},

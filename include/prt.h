@@ -107,6 +107,10 @@ typedef struct {
     uint64_t node_visits, tri_tests;    /* only counted by PRT_TRACE_COUNT launches */
     uint64_t flagged_rays;              /* rays re-resolved in FP64 by PRT_TRACE_EXACT */
     uint64_t paths;
+    /* SIMT utilisation of the persistent traversal loop (PRT_TRACE_COUNT launches only):
+     * loop iterations per warp, lanes doing a record visit summed over iterations, leaf
+     * phases and lanes intersecting in them */
+    uint64_t warp_iters, node_lane_iters, leaf_phases, leaf_lane_phases;
 } prt_counters;
 
 /* trace flags */

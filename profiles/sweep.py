@@ -23,6 +23,9 @@ def measure(ctx, r, hits, reps=3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); ctx.trace_closest(r, N, hits, 0); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
+    if c["warp_iters"]:
+        print(f"    util: iters/warp-ray {c['warp_iters'] * 32 / N:.1f}  node lanes/iter {c['node_lane_iters'] / c['warp_iters']:.1f}  "
+              f"leaf phases/iter {c['leaf_phases'] / c['warp_iters']:.3f}  lanes/leaf phase {c['leaf_lane_phases'] / max(1, c['leaf_phases']):.1f}")
     return N / best / 1e3, c["node_visits"] / N, c["tri_tests"] / N
 
 def main():
@@ -40,6 +43,34 @@ def main():
                     st = ctx.build_bvh(max_leaf_tris=leaf, cost_node=cn, cost_tri=ct, rotations=rot)
                     m, nn, nt = measure(ctx, r, hits)
                     print(f"leaf {leaf} cn {cn} ct {ct} rot {rot}: {m:8.1f} Mrays/s  N_node {nn:6.1f} N_tri {nt:5.1f} nodes {st['n_nodes']} depth {st['depth']} sah {st['sah_cost']:.1f} build {st['ms_total']:.2f} ms", flush=True)
+    elif mode == "util":
+        ctx = _abi.Context(0)
+        ctx.set_triangles_dev(tris, 1_000_000)
+        print(ctx.build_bvh(max_leaf_tris=1))
+        print(measure(ctx, r, hits))
+    elif mode == "render":
+        from pyrenderer_b200.io_utils.read_tungsten import read_file
+        from pyrenderer_b200.main import DEFAULT_SCENE
+        scene, cam = read_file(DEFAULT_SCENE)
+        a = scene.arrays()
+        for ri, lb in ((6, 8), (16, 4), (10, 33), (16, 33), (16, 16), (24, 33), (16, 8), (12, 12), (20, 20)):
+            os.environ["PRT_REFILL_IDLE"] = str(ri); os.environ["PRT_LEAF_BATCH"] = str(lb)
+            ctx = _abi.Context(0)
+            ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])
+            ctx.build_bvh()
+            iview, sw, sh, focal, W, H = cam.device_record()
+            ctx.set_camera(iview, sw, sh, focal, W, H)
+            acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+            best = 1e9
+            for rep in range(3):
+                ctx.reset_counters()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); ctx.render(ctx.render_params(seed=1, spp_begin=8 * rep, spp_end=8 * rep + 8, max_depth=8), acc); e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            c = ctx.counters()
+            print(f"render refill_idle {ri:2d} leaf_batch {lb:2d}: {best:7.2f} ms / 8 spp  {(c['rays_closest'] + c['rays_shadow']) / best / 1e3:8.1f} Mrays/s", flush=True)
+            ctx.close()
     else:
         for ri in (2, 4, 6, 8, 12, 16):
             for lb in (1, 4, 6, 8, 12, 16):

@@ -50,7 +50,9 @@ class PrtBvhOptions(C.Structure):
 class PrtCounters(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("flagged_rays", C.c_uint64), ("paths", C.c_uint64)]
+                ("flagged_rays", C.c_uint64), ("paths", C.c_uint64), ("warp_iters", C.c_uint64),
+                ("node_lane_iters", C.c_uint64), ("leaf_phases", C.c_uint64),
+                ("leaf_lane_phases", C.c_uint64)]
 
 
 EXPORTS = [

@@ -32,6 +32,7 @@ __device__ __forceinline__ float clamp_dir(float d) {
 
 struct RayBox {  // per-ray constants of the slab test
     float3 o, idir;
+    uint32_t selx, sely, selz;  // PRMT selectors: bytes -> (near0, far0, near1, far1) for this ray's octant
 };
 
 __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
@@ -39,6 +40,9 @@ __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
     r.o = o;
     r.idir = make_float3(__fdiv_rn(1.0f, clamp_dir(d.x)), __fdiv_rn(1.0f, clamp_dir(d.y)),
                          __fdiv_rn(1.0f, clamp_dir(d.z)));
+    r.selx = d.x < 0.0f ? 0x2301u : 0x3210u;
+    r.sely = d.y < 0.0f ? 0x2301u : 0x3210u;
+    r.selz = d.z < 0.0f ? 0x2301u : 0x3210u;
     return r;
 }
 
@@ -47,36 +51,36 @@ __device__ __forceinline__ float qf(uint32_t w, int byte) {
 }
 
 // Slab test of both children.  Returns hit mask (bit0 child0, bit1 child1) and
-// entry distances.  EXACT widens every interval by the forward error bound.
+// entry distances.  Each axis word holds (c0.lo, c0.hi, c1.lo, c1.hi); one PRMT with the
+// ray's octant selector turns it into (near0, far0, near1, far1), so no per-plane min/max
+// is needed: t = q * (scale/d) + (o - ray.o)/d is already the near / far distance.
+// EXACT widens every interval by the forward error bound.
 template <bool EXACT>
 __device__ __forceinline__ int node_test(const float4 n0, const float4 n1, const RayBox& r,
                                          float tmin, float tmax, float& t0, float& t1) {
-    uint32_t em = __float_as_uint(n0.w);
-    uint32_t q0 = __float_as_uint(n1.x), q1 = __float_as_uint(n1.y), q2 = __float_as_uint(n1.z);
-    float sx = __uint_as_float((em & 0xffu) << 23);
-    float sy = __uint_as_float(((em >> 8) & 0xffu) << 23);
-    float sz = __uint_as_float(((em >> 16) & 0xffu) << 23);
-    float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
-    float bx = (n0.x - r.o.x) * r.idir.x, by = (n0.y - r.o.y) * r.idir.y,
-          bz = (n0.z - r.o.z) * r.idir.z;
-    // child0: lo = q0.b0..b2, hi = q0.b3, q1.b0, q1.b1 ; child1: lo = q1.b2, q1.b3, q2.b0 ; hi = q2.b1..b3
-    float c0lx = fmaf(qf(q0, 0), ax, bx), c0ly = fmaf(qf(q0, 1), ay, by), c0lz = fmaf(qf(q0, 2), az, bz);
-    float c0hx = fmaf(qf(q0, 3), ax, bx), c0hy = fmaf(qf(q1, 0), ay, by), c0hz = fmaf(qf(q1, 1), az, bz);
-    float c1lx = fmaf(qf(q1, 2), ax, bx), c1ly = fmaf(qf(q1, 3), ay, by), c1lz = fmaf(qf(q2, 0), az, bz);
-    float c1hx = fmaf(qf(q2, 1), ax, bx), c1hy = fmaf(qf(q2, 2), ay, by), c1hz = fmaf(qf(q2, 3), az, bz);
-    float n0t = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), tmin));
-    float f0t = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fminf(fmaxf(c0lz, c0hz), tmax));
-    float n1t = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), tmin));
-    float f1t = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fminf(fmaxf(c1lz, c1hz), tmax));
+    const uint32_t em = __float_as_uint(n0.w);
+    const uint32_t qx = __byte_perm(__float_as_uint(n1.x), 0u, r.selx);
+    const uint32_t qy = __byte_perm(__float_as_uint(n1.y), 0u, r.sely);
+    const uint32_t qz = __byte_perm(__float_as_uint(n1.z), 0u, r.selz);
+    const float sx = __uint_as_float((em & 0xffu) << 23);
+    const float sy = __uint_as_float(((em >> 8) & 0xffu) << 23);
+    const float sz = __uint_as_float(((em >> 16) & 0xffu) << 23);
+    const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
+    const float bx = (n0.x - r.o.x) * r.idir.x, by = (n0.y - r.o.y) * r.idir.y,
+                bz = (n0.z - r.o.z) * r.idir.z;
+    float n0t = fmaxf(fmaxf(fmaf(qf(qx, 0), ax, bx), fmaf(qf(qy, 0), ay, by)), fmaxf(fmaf(qf(qz, 0), az, bz), tmin));
+    float f0t = fminf(fminf(fmaf(qf(qx, 1), ax, bx), fmaf(qf(qy, 1), ay, by)), fminf(fmaf(qf(qz, 1), az, bz), tmax));
+    float n1t = fmaxf(fmaxf(fmaf(qf(qx, 2), ax, bx), fmaf(qf(qy, 2), ay, by)), fmaxf(fmaf(qf(qz, 2), az, bz), tmin));
+    float f1t = fminf(fminf(fmaf(qf(qx, 3), ax, bx), fmaf(qf(qy, 3), ay, by)), fminf(fmaf(qf(qz, 3), az, bz), tmax));
     if (EXACT) {
         float m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(bx) + 255.0f * fabsf(ax), fabsf(by) + 255.0f * fabsf(ay)),
                                         fabsf(bz) + 255.0f * fabsf(az)));
         n0t -= m; n1t -= m; f0t += m; f1t += m;
     }
     t0 = n0t; t1 = n1t;
-    uint32_t meta = em >> 24;
-    int h0 = (n0t <= f0t) && ((meta & 0xFu) != 0xFu);
-    int h1 = (n1t <= f1t) && ((meta >> 4) != 0xFu);
+    const uint32_t meta = em >> 24;
+    const int h0 = (n0t <= f0t) && ((meta & 0xFu) != 0xFu);
+    const int h1 = (n1t <= f1t) && ((meta >> 4) != 0xFu);
     return h0 | (h1 << 1);
 }
 

@@ -334,9 +334,10 @@ __global__ void emit_kernel(const float4* __restrict__ verts, const uint32_t* __
     Node32 nd;
     nd.ox = o[0]; nd.oy = o[1]; nd.oz = o[2];
     nd.em = e[0] | (e[1] << 8) | (e[2] << 16) | (c0 << 24) | (c1 << 28);
-    nd.q0 = q[0][0][0] | (q[0][0][1] << 8) | (q[0][0][2] << 16) | (q[0][1][0] << 24);
-    nd.q1 = q[0][1][1] | (q[0][1][2] << 8) | (q[1][0][0] << 16) | (q[1][0][1] << 24);
-    nd.q2 = q[1][0][2] | (q[1][1][0] << 8) | (q[1][1][1] << 16) | (q[1][1][2] << 24);
+    // one word per axis: child0.lo | child0.hi << 8 | child1.lo << 16 | child1.hi << 24
+    nd.q0 = q[0][0][0] | (q[0][1][0] << 8) | (q[1][0][0] << 16) | (q[1][1][0] << 24);
+    nd.q1 = q[0][0][1] | (q[0][1][1] << 8) | (q[1][0][1] << 16) | (q[1][1][1] << 24);
+    nd.q2 = q[0][0][2] | (q[0][1][2] << 8) | (q[1][0][2] << 16) | (q[1][1][2] << 24);
     if (!lleaf && !rleaf) nd.link = idx + 1 + icount[l];
     else if (lleaf) nd.link = tstart;
     else nd.link = tstart + tcount[l];
@@ -358,9 +359,9 @@ __global__ void emit_single_kernel(const float4* __restrict__ verts, Node32* nod
     Node32 nd;
     nd.ox = o[0]; nd.oy = o[1]; nd.oz = o[2];
     nd.em = e[0] | (e[1] << 8) | (e[2] << 16) | (1u << 24) | (0xFu << 28);
-    nd.q0 = ql[0] | (ql[1] << 8) | (ql[2] << 16) | (qh[0] << 24);
-    nd.q1 = qh[1] | (qh[2] << 8);
-    nd.q2 = 0;
+    nd.q0 = ql[0] | (qh[0] << 8);
+    nd.q1 = ql[1] | (qh[1] << 8);
+    nd.q2 = ql[2] | (qh[2] << 8);
     nd.link = 0;
     nodes[0] = nd;
     tris_out[0] = verts[0]; tris_out[1] = verts[1]; tris_out[2] = verts[2];

@@ -20,9 +20,9 @@ constexpr uint32_t kLeafFlag = 0x80000000u;
 struct Node32 {        // 32 B, two float4 / one sector
     float ox, oy, oz;  // frame origin
     uint32_t em;       // ex | ey<<8 | ez<<16 | meta<<24   (scale = 2^(e-127)); meta: cnt0 | cnt1<<4
-    uint32_t q0;       // child0: lo.x lo.y lo.z hi.x
-    uint32_t q1;       // child0: hi.y hi.z | child1: lo.x lo.y
-    uint32_t q2;       // child1: lo.z hi.x hi.y hi.z
+    uint32_t q0;       // x planes: child0.lo, child0.hi, child1.lo, child1.hi (one byte each)
+    uint32_t q1;       // y planes, same order
+    uint32_t q2;       // z planes, same order
     uint32_t link;     // see bvh.cuh
 };
 static_assert(sizeof(Node32) == 32, "node must be 32 bytes");
@@ -40,6 +40,7 @@ struct SceneDev {
 
 struct Counters {
     unsigned long long rays_closest, rays_shadow, node_visits, tri_tests, flagged_rays, paths;
+    unsigned long long warp_iters, node_lane_iters, leaf_phases, leaf_lane_phases;  // persist.cuh utilisation (COUNT)
 };
 
 // ---- small vector helpers ---------------------------------------------------

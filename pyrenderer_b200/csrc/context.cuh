@@ -39,7 +39,7 @@ struct prt_ctx {
     unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
     unsigned fetch_next = 0;
     int grid_persist = 0;
-    int refill_idle = 6, leaf_batch = 6;
+    int refill_idle = 0, leaf_batch = 8;  // refill_idle 0 = by scene size (profiles/r1_sweeps.txt)
 
     // device staging of the *_host entry points (grow-only, reused across calls)
     void* stage[2] = {nullptr, nullptr};
@@ -67,7 +67,9 @@ struct prt_ctx {
         s.light_tris = light_tris;
         s.verts_gid = verts_gid;
         s.nt = nt; s.n_nodes = n_nodes; s.nl = nl; s.nm = nm;
-        s.refill_idle = refill_idle; s.leaf_batch = leaf_batch;
+        // short traversals (tiny scenes) amortise the ray set-up over more lanes per refill
+        s.refill_idle = refill_idle > 0 ? refill_idle : (n_nodes < 4096 ? 16 : 6);
+        s.leaf_batch = leaf_batch;
         return s;
     }
 };

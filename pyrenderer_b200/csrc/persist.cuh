@@ -80,6 +80,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
     int bgid = -1, sp = 0;
     uint32_t cur = kDone, tag = 0;
     unsigned long long c_nodes = 0, c_tris = 0, c_rays = 0;
+    unsigned long long c_iters = 0, c_nlanes = 0, c_lphases = 0, c_llanes = 0;  // lane 0 only
 
     if (sc.n_nodes == 0) {  // empty scene: everything misses
         for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -117,7 +118,13 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
         }
         if (exhausted && __ballot_sync(FULL, has_ray) == 0) break;  // (idle mask may be stale after a refill)
 
+        if (COUNT) {
+            ++c_iters;
+            c_nlanes += __popc(__ballot_sync(FULL, has_ray && !(cur & kLeafFlag)));
+        }
         // ---- one record visit for every lane that is at an internal record
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep)
         if (has_ray && !(cur & kLeafFlag)) {
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
@@ -148,6 +155,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
         // idle lanes keep cur == kDone, so "no leaf flag" == "still walking records"
         const unsigned nodem = ~__ballot_sync(FULL, (cur & kLeafFlag) != 0u);
         if (leafm && (__popc(leafm) >= sc.leaf_batch || nodem == 0)) {
+            if (COUNT) { ++c_lphases; c_llanes += __popc(leafm); }
             if (at_leaf) {
                 const uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
                 bool stop = false;
@@ -185,6 +193,10 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
             atomicAdd(&ctr->node_visits, c_nodes);
             atomicAdd(&ctr->tri_tests, c_tris);
             atomicAdd(MODE == MODE_ANY ? &ctr->rays_shadow : &ctr->rays_closest, c_rays);
+            atomicAdd(&ctr->warp_iters, c_iters);
+            atomicAdd(&ctr->node_lane_iters, c_nlanes);
+            atomicAdd(&ctr->leaf_phases, c_lphases);
+            atomicAdd(&ctr->leaf_lane_phases, c_llanes);
         }
     }
 }

@@ -332,6 +332,8 @@ int prt_get_counters(prt_ctx* ctx, prt_counters* out) {
     out->rays_closest = c.rays_closest; out->rays_shadow = c.rays_shadow;
     out->node_visits = c.node_visits; out->tri_tests = c.tri_tests;
     out->flagged_rays = c.flagged_rays; out->paths = c.paths;
+    out->warp_iters = c.warp_iters; out->node_lane_iters = c.node_lane_iters;
+    out->leaf_phases = c.leaf_phases; out->leaf_lane_phases = c.leaf_lane_phases;
     return PRT_OK;
 }
 
