@@ -48,12 +48,12 @@ def main():
         ctx.set_triangles_dev(tris, 1_000_000)
         print(ctx.build_bvh(max_leaf_tris=1))
         print(measure(ctx, r, hits))
-    elif mode == "render":
+    elif mode in ("render", "render1"):
         from pyrenderer_b200.io_utils.read_tungsten import read_file
         from pyrenderer_b200.main import DEFAULT_SCENE
         scene, cam = read_file(DEFAULT_SCENE)
         a = scene.arrays()
-        for ri, lb in ((6, 8), (16, 4), (10, 33), (16, 33), (16, 16), (24, 33), (16, 8), (12, 12), (20, 20)):
+        for ri, lb in (((6, 8), (16, 4), (10, 33), (16, 33), (16, 16), (24, 33), (16, 8), (12, 12), (20, 20)) if mode == "render" else ((16, 8),)):
             os.environ["PRT_REFILL_IDLE"] = str(ri); os.environ["PRT_LEAF_BATCH"] = str(lb)
             ctx = _abi.Context(0)
             ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])

@@ -77,7 +77,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.build()
+    path = os.environ.get("PRT_LIB") or _build.build()  # PRT_LIB: a tuning variant built by profiles/
     lib = C.CDLL(path)
     vp, u32, u64, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float
     lib.prt_abi_version.restype = C.c_int

@@ -35,15 +35,19 @@ def _newest_input():
     return t
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_input():
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants (profiles/sweep.py), e.g. defines=("-DPRT_PSTACK=8",)."""
+    global OBJ
+    lib = out or LIB
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _newest_input():
+        return lib
+    obj_dir = OBJ if out is None else OBJ + "_" + os.path.basename(out)
+    os.makedirs(obj_dir, exist_ok=True)
     exe = nvcc()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + list(defines)
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         cmd = [exe] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
@@ -56,12 +60,12 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}")
             objs.append(obj)
-    cmd = [exe, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [exe, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link of libprt.so failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -80,12 +80,26 @@ def resolve(accum):
     return a[..., :3] / n
 
 
+def reinhard_extended(img):
+    """Extended Reinhard on luminance, white point = max luminance
+    (reference: main_taichi.py:53-59,67-78 == tone_map.py:17-33)."""
+    lum = img[..., 0] * 0.2126 + img[..., 1] * 0.7152 + img[..., 2] * 0.0722
+    white = float(np.max(lum)) if lum.size else 1.0
+    if not white > 0.0:
+        return img.copy()
+    l_new = lum * (1.0 + lum / (white * white)) / (1.0 + lum)
+    scale = np.divide(l_new, lum, out=np.zeros_like(lum), where=lum > 0)
+    return img * scale[..., None]
+
+
 def to_image(accum, tonemap=None):
-    """Mean radiance as the reference stores it: ``image[W-1-j, i]`` (main.py:55),
-    i.e. top row first.  tonemap: None (main.py), "sqrt" (main_taichi.py:61-64)."""
+    """Mean radiance as the reference stores it: ``image[W-1-j, i]`` (main.py:55), i.e. top row
+    first.  tonemap: None (main.py), "sqrt" (main_taichi.py:61-64), "reinhard"."""
     img = resolve(accum)[::-1]
     if tonemap == "sqrt":
         img = np.sqrt(np.maximum(img, 0.0))
+    elif tonemap == "reinhard":
+        img = reinhard_extended(np.maximum(img, 0.0))
     return np.ascontiguousarray(img)
 
 

@@ -304,16 +304,21 @@ int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_
     USE_DEVICE(ctx);
     if (!params || !accum_host) { ctx->set_error("render: NULL argument"); return PRT_ERR_INVALID; }
     if (!ctx->cam_set) { ctx->set_error("render: camera not set"); return PRT_ERR_STATE; }
-    size_t bytes = sizeof(float) * 4 * (size_t)ctx->cam.width * ctx->cam.height;
-    float* d = nullptr;
-    PRT_CUDA_TRY(ctx, cudaMalloc(&d, bytes));
-    cudaError_t e = cudaMemcpy(d, accum_host, bytes, cudaMemcpyHostToDevice);
-    int rc = PRT_OK;
-    if (e == cudaSuccess) rc = render(ctx, params, d, nullptr, 0);
-    if (e == cudaSuccess && rc == PRT_OK) e = cudaMemcpy(accum_host, d, bytes, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) { ctx->set_error("render_host: %s", cudaGetErrorString(e)); return PRT_ERR_CUDA; }
-    return rc;
+    const size_t bytes = sizeof(float) * 4 * (size_t)ctx->cam.width * ctx->cam.height;
+    int rc = stage_reserve(ctx, 0, bytes);  // grow-only device staging, reused across calls
+    if (rc != PRT_OK) return rc;
+    if (!ctx->copy_stream[0]) PRT_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream[0], cudaStreamNonBlocking));
+    cudaStream_t s = ctx->copy_stream[0];
+    float* d = (float*)ctx->stage[0];
+    // synchronous entry point: earlier asynchronous work on other streams may still use the
+    // context's wavefront buffers
+    PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    PRT_CUDA_TRY(ctx, cudaMemcpyAsync(d, accum_host, bytes, cudaMemcpyHostToDevice, s));
+    rc = render(ctx, params, d, nullptr, s);
+    if (rc != PRT_OK) return rc;
+    PRT_CUDA_TRY(ctx, cudaMemcpyAsync(accum_host, d, bytes, cudaMemcpyDeviceToHost, s));
+    PRT_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return PRT_OK;
 }
 
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths) {

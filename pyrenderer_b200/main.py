@@ -64,6 +64,6 @@ if __name__ == "__main__":
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default="test.png")
-    ap.add_argument("--tonemap", default=None, choices=[None, "sqrt"])
+    ap.add_argument("--tonemap", default=None, choices=[None, "sqrt", "reinhard"])
     a = ap.parse_args()
     main(a.scene, a.samples, a.max_depth, a.width, a.height, a.seed, a.out, a.tonemap)

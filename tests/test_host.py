@@ -164,3 +164,49 @@ def test_oracle_light_hit_known_answer(cornell):
     assert np.allclose(mean[on_light], np.array([0.9, 0.85, 0.7], np.float32).astype(np.float64), atol=1e-12)
     assert stats[0] > W * H * 4 and stats[1] > 0
     assert np.all(mean >= 0) and np.isfinite(mean).all()
+
+
+def test_subdivision_utility(cornell):
+    from pyrenderer_b200.mathematics.subdivide import subdivide, subdivide_scene_arrays
+    scene, _ = cornell
+    a = scene.arrays()
+    t, parent = subdivide(a["tris"], 3)
+    assert t.shape == (36 * 64, 3, 3) and np.array_equal(np.bincount(parent), np.full(36, 64))
+    area = lambda x: 0.5 * np.linalg.norm(np.cross(x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]), axis=1)
+    assert np.allclose(np.bincount(parent, weights=area(t)), area(a["tris"]), rtol=1e-5)
+    # children keep the parent's orientation (normals) and shared edges get identical midpoints
+    n_child = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    n_par = np.cross(a["tris"][:, 1] - a["tris"][:, 0], a["tris"][:, 2] - a["tris"][:, 0])[parent]
+    assert np.all(np.einsum("ij,ij->i", n_child, n_par) > 0)
+    verts = np.unique(t.reshape(-1, 3), axis=0)
+    assert verts.shape[0] < t.shape[0] * 3 / 3.5  # welded: ~6 triangles share a vertex
+    b = subdivide_scene_arrays(a, np.where(np.isin(a["tri_prim"], [5, 6]), 1, 2))
+    assert b["tris"].shape[0] == 12 * 16 + 24 * 4
+    assert np.array_equal(np.unique(b["tri_material"][b["light_tris"]]), [7])
+    assert b["light_tris"].shape[0] == 2 * 16
+
+
+def test_output_stage(tmp_path):
+    from pyrenderer_b200.core import tracing
+    from pyrenderer_b200.main import write_png
+    acc = np.zeros((4, 6, 4), np.float32)
+    acc[..., 3] = 2.0
+    acc[0, :, :3] = 2.0    # bottom row (v = 0) -> mean 1.0
+    acc[3, 0, :3] = 8.0    # top-left -> mean 4.0 (would wrap in the reference's uint8 cast)
+    img = tracing.to_image(acc)
+    assert img.shape == (4, 6, 3) and img[3, 2, 0] == 1.0 and img[0, 0, 0] == 4.0  # row flip, main.py:55
+    assert np.allclose(tracing.to_image(acc, "sqrt")[0, 0], 2.0)
+    r = tracing.to_image(acc, "reinhard")
+    assert np.allclose(r[0, 0], 1.0, atol=1e-6) and 0 < r[3, 2, 0] < 1.0   # white point maps to 1
+    u8 = tracing.to_uint8(img)
+    assert u8[0, 0, 0] == 255 and u8[3, 2, 0] == 255 and u8[1, 1, 0] == 0   # clamp, not wrap-around
+    p = tmp_path / "o.png"
+    write_png(str(p), u8)
+    data = p.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and b"IHDR" in data and b"IEND" in data
+    try:
+        import cv2
+        back = cv2.imread(str(p))[..., ::-1]
+        assert np.array_equal(back, u8)
+    except ImportError:
+        pass
