@@ -1,30 +1,30 @@
-// bvh.cuh -- the 32-byte quantised node and the traversal loop.
+// bvh.cuh -- the quantised 4-wide node, its slab test and the per-lane stack.
 //
-// Node32 (common.cuh) holds the boxes of its TWO children, quantised to 8 bits
-// per plane in the node's own frame: plane = o + q * 2^(e-127).  The builder
-// (bvh_build.cu) rounds lo down / hi up against this exact decode expression,
-// so decoded boxes always contain the child's true FP32 box.  The slab test
-// never decodes the box: per axis it forms a = scale/d and b = (o - ray.o)/d once
-// and each of the 12 planes costs one cvt + one FMA (t = q*a + b).
+// Node64 (common.cuh) holds the boxes of up to FOUR children, quantised to 8 bits per
+// plane in the node's own frame: plane = o + q * 2^(e-127).  The builder (bvh_build.cu)
+// rounds lo down / hi up against this exact decode expression, so a decoded box always
+// contains the child's true FP32 box.  The slab test never decodes a box: per axis it
+// forms a = scale/d and b = (o - ray.o)/d once and each of the 24 planes costs one
+// I2F.U8 + one FMA (t = q*a + b).  Planes are stored as one word of four "lo" bytes and
+// one word of four "hi" bytes per axis; the ray's octant picks which word is the near
+// side, so no per-plane min/max is needed.
 //
-// Records are stored in DFS pre-order, triangles in DFS leaf order, which lets
-// one 32-bit `link` address both children:
-//   both internal : child0 = self+1,            child1 = link
-//   one leaf      : internal child = self+1,    leaf triangles start at link
-//   both leaves   : leaf0 starts at link,       leaf1 at link + cnt0
-// meta = cnt0 | cnt1<<4 (cnt == 0 means "internal"; 0xF means "absent").
+// Child references are explicit (record index, or kLeafFlag | first_tri << 3 | count for
+// a leaf of 1..7 triangles stored contiguously, or kNoChild).
 //
 // Replaces: BVH.hit_helper accelerators/bvh.py:218-231 (recursive, unordered),
-// World.hit_all mathematics/intersection_taichi.py:238-291 (threaded "next"
-// links) and the slab tests mathematics/bbox.py:6-26 /
-// accelerators/bvh_taichi.py:168-190.
+// World.hit_all mathematics/intersection_taichi.py:238-291 (threaded "next" links) and
+// the slab tests mathematics/bbox.py:6-26 / accelerators/bvh_taichi.py:168-190.
 #pragma once
 #include "common.cuh"
 #include "intersect.cuh"
 
 namespace prt {
 
-constexpr int kMaxStack = 96;  // builder guarantees tree depth < kMaxStack
+constexpr int kMaxStack = 128;  // the builder guarantees 3 * depth + 1 <= kMaxStack
+constexpr int kPStack = 16;     // levels kept in shared memory; deeper ones in local memory
+constexpr int kPStackOvf = kMaxStack - kPStack;
+constexpr uint32_t kDone = kNoChild;  // has kLeafFlag set
 
 __device__ __forceinline__ float clamp_dir(float d) {
     return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
@@ -32,7 +32,7 @@ __device__ __forceinline__ float clamp_dir(float d) {
 
 struct RayBox {  // per-ray constants of the slab test
     float3 o, idir;
-    uint32_t selx, sely, selz;  // PRMT selectors: bytes -> (near0, far0, near1, far1) for this ray's octant
+    bool negx, negy, negz;
 };
 
 __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
@@ -40,79 +40,114 @@ __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
     r.o = o;
     r.idir = make_float3(__fdiv_rn(1.0f, clamp_dir(d.x)), __fdiv_rn(1.0f, clamp_dir(d.y)),
                          __fdiv_rn(1.0f, clamp_dir(d.z)));
-    r.selx = d.x < 0.0f ? 0x2301u : 0x3210u;
-    r.sely = d.y < 0.0f ? 0x2301u : 0x3210u;
-    r.selz = d.z < 0.0f ? 0x2301u : 0x3210u;
+    r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
     return r;
 }
 
 __device__ __forceinline__ float qf(uint32_t w, int byte) {
-    return (float)((w >> (8 * byte)) & 0xffu);
+    return (float)((w >> (8 * byte)) & 0xffu);  // I2F.U8 with a static byte selector
 }
 
-// Slab test of both children.  Returns hit mask (bit0 child0, bit1 child1) and
-// entry distances.  Each axis word holds (c0.lo, c0.hi, c1.lo, c1.hi); one PRMT with the
-// ray's octant selector turns it into (near0, far0, near1, far1), so no per-plane min/max
-// is needed: t = q * (scale/d) + (o - ray.o)/d is already the near / far distance.
-// EXACT widens every interval by the forward error bound.
-template <bool EXACT>
-__device__ __forceinline__ int node_test(const float4 n0, const float4 n1, const RayBox& r,
-                                         float tmin, float tmax, float& t0, float& t1) {
-    const uint32_t em = __float_as_uint(n0.w);
-    const uint32_t qx = __byte_perm(__float_as_uint(n1.x), 0u, r.selx);
-    const uint32_t qy = __byte_perm(__float_as_uint(n1.y), 0u, r.sely);
-    const uint32_t qz = __byte_perm(__float_as_uint(n1.z), 0u, r.selz);
-    const float sx = __uint_as_float((em & 0xffu) << 23);
-    const float sy = __uint_as_float(((em >> 8) & 0xffu) << 23);
-    const float sz = __uint_as_float(((em >> 16) & 0xffu) << 23);
-    const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
-    const float bx = (n0.x - r.o.x) * r.idir.x, by = (n0.y - r.o.y) * r.idir.y,
-                bz = (n0.z - r.o.z) * r.idir.z;
-    float n0t = fmaxf(fmaxf(fmaf(qf(qx, 0), ax, bx), fmaf(qf(qy, 0), ay, by)), fmaxf(fmaf(qf(qz, 0), az, bz), tmin));
-    float f0t = fminf(fminf(fmaf(qf(qx, 1), ax, bx), fmaf(qf(qy, 1), ay, by)), fminf(fmaf(qf(qz, 1), az, bz), tmax));
-    float n1t = fmaxf(fmaxf(fmaf(qf(qx, 2), ax, bx), fmaf(qf(qy, 2), ay, by)), fmaxf(fmaf(qf(qz, 2), az, bz), tmin));
-    float f1t = fminf(fminf(fmaf(qf(qx, 3), ax, bx), fmaf(qf(qy, 3), ay, by)), fminf(fmaf(qf(qz, 3), az, bz), tmax));
-    if (EXACT) {
-        float m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(bx) + 255.0f * fabsf(ax), fabsf(by) + 255.0f * fabsf(ay)),
-                                        fabsf(bz) + 255.0f * fabsf(az)));
-        n0t -= m; n1t -= m; f0t += m; f1t += m;
-    }
-    t0 = n0t; t1 = n1t;
-    const uint32_t meta = em >> 24;
-    const int h0 = (n0t <= f0t) && ((meta & 0xFu) != 0xFu);
-    const int h1 = (n1t <= f1t) && ((meta >> 4) != 0xFu);
-    return h0 | (h1 << 1);
-}
-
-__device__ __forceinline__ void node_refs(uint32_t self, uint32_t em, uint32_t link, uint32_t& r0,
-                                          uint32_t& r1) {
-    uint32_t c0 = (em >> 24) & 0xFu, c1 = em >> 28;
-    if (c0 == 0xFu) c0 = 1;  // absent children never pass node_test; value irrelevant
-    if (c1 == 0xFu) c1 = 1;
-    if (c0 == 0) {
-        r0 = self + 1;
-        r1 = c1 == 0 ? link : (kLeafFlag | (link << 3) | c1);
-    } else {
-        r0 = kLeafFlag | (link << 3) | c0;
-        r1 = c1 == 0 ? self + 1 : (kLeafFlag | ((link + c0) << 3) | c1);
-    }
-}
-
-// Per-thread traversal stack: the first kSmemStack levels live in shared memory
-// ([level][thread], conflict-free), deeper levels spill to a local array.
-struct Stack {
-    uint32_t* smem;  // &s_stack[0][threadIdx.x]
-    uint32_t ovf[kMaxStack - kSmemStack];
-    int sp;
-    __device__ __forceinline__ void push(uint32_t v) {
-        if (sp < kSmemStack) smem[sp * kTraceThreads] = v;
-        else ovf[sp - kSmemStack] = v;
-        ++sp;
-    }
-    __device__ __forceinline__ uint32_t pop() {
-        --sp;
-        return sp < kSmemStack ? smem[sp * kTraceThreads] : ovf[sp - kSmemStack];
-    }
+struct NodeHits {
+    float t[4];       // entry distance per child (valid where the mask bit is set)
+    uint32_t ref[4];
 };
+
+// Slab test of the four children.  Returns the hit mask.  EXACT widens every interval by
+// the forward error bound of t = q*a + b so that no box the exact ray touches is missed.
+template <bool EXACT>
+__device__ __forceinline__ int node_test4(const Node64* __restrict__ node, const RayBox& r,
+                                          float tmin, float tmax, NodeHits& h) {
+    const uint4* np = reinterpret_cast<const uint4*>(node);
+    const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), w2 = __ldg(np + 2), w3 = __ldg(np + 3);
+    const float sx = __uint_as_float((w0.w & 0xffu) << 23);
+    const float sy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23);
+    const float sz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23);
+    const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
+    const float bx = (__uint_as_float(w0.x) - r.o.x) * r.idir.x, by = (__uint_as_float(w0.y) - r.o.y) * r.idir.y,
+                bz = (__uint_as_float(w0.z) - r.o.z) * r.idir.z;
+    const uint32_t nx = r.negx ? w1.y : w1.x, fx = r.negx ? w1.x : w1.y;
+    const uint32_t ny = r.negy ? w1.w : w1.z, fy = r.negy ? w1.z : w1.w;
+    const uint32_t nz = r.negz ? w2.y : w2.x, fz = r.negz ? w2.x : w2.y;
+    h.ref[0] = w2.z; h.ref[1] = w2.w; h.ref[2] = w3.x; h.ref[3] = w3.y;
+    float m = 0.0f;
+    if (EXACT)
+        m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(bx) + 255.0f * fabsf(ax), fabsf(by) + 255.0f * fabsf(ay)),
+                                  fabsf(bz) + 255.0f * fabsf(az)));
+    int mask = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float tn = fmaxf(fmaxf(fmaf(qf(nx, c), ax, bx), fmaf(qf(ny, c), ay, by)), fmaxf(fmaf(qf(nz, c), az, bz), tmin));
+        float tf = fminf(fminf(fmaf(qf(fx, c), ax, bx), fmaf(qf(fy, c), ay, by)), fminf(fmaf(qf(fz, c), az, bz), tmax));
+        if (EXACT) { tn -= m; tf += m; }
+        h.t[c] = tn;
+        if (tn <= tf && h.ref[c] != kNoChild) mask |= 1 << c;
+    }
+    return mask;
+}
+
+// ---- per-lane stack of (child reference, entry distance) pairs -----------------------
+// kPStack levels in shared memory ([level][lane] of 8-byte slots, conflict-free), deeper
+// levels in local memory.  Keeping the entry distance lets a pop discard, without touching
+// memory, every subtree that a closer hit found in the meantime has made irrelevant.
+__device__ __forceinline__ void sstack_push(uint32_t saddr, uint2* ovf, int& sp, uint32_t ref, float t) {
+    if (sp < kPStack)
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)), "r"(ref), "r"(__float_as_uint(t)) : "memory");
+    else
+        ovf[sp - kPStack] = make_uint2(ref, __float_as_uint(t));
+    ++sp;
+}
+__device__ __forceinline__ uint32_t sstack_pop(uint32_t saddr, const uint2* ovf, int& sp, float& t) {
+    --sp;
+    uint32_t ref, tb;
+    if (sp < kPStack) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)) : "memory");
+    } else {
+        uint2 e = ovf[sp - kPStack];
+        ref = e.x; tb = e.y;
+    }
+    t = __uint_as_float(tb);
+    return ref;
+}
+// pop until an entry that can still beat `bound` (or the stack is empty -> kDone)
+__device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, const uint2* ovf, int& sp, float bound) {
+    while (sp > 0) {
+        float t;
+        const uint32_t ref = sstack_pop(saddr, ovf, sp, t);
+        if (t <= bound) return ref;
+    }
+    return kDone;
+}
+
+__device__ __forceinline__ void cswap(float& ta, uint32_t& ra, float& tb, uint32_t& rb) {
+    const bool s = tb < ta;
+    const float t0 = s ? tb : ta, t1 = s ? ta : tb;
+    const uint32_t r0 = s ? rb : ra, r1 = s ? ra : rb;
+    ta = t0; tb = t1; ra = r0; rb = r1;
+}
+
+// Continue after a node visit: the nearest hit child becomes the next reference, the others
+// are pushed far-first (so the nearer ones pop first); no hit -> pop.
+__device__ __forceinline__ uint32_t descend(int mask, NodeHits& h, uint32_t saddr, uint2* ovf, int& sp,
+                                            float bound) {
+    if (mask == 0) return sstack_pop_live(saddr, ovf, sp, bound);
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (!(mask & (1 << c))) h.t[c] = inf;
+    if (mask & (mask - 1)) {  // two or more hits: sorting network for 4 (misses sort to the back)
+        cswap(h.t[0], h.ref[0], h.t[1], h.ref[1]);
+        cswap(h.t[2], h.ref[2], h.t[3], h.ref[3]);
+        cswap(h.t[0], h.ref[0], h.t[2], h.ref[2]);
+        cswap(h.t[1], h.ref[1], h.t[3], h.ref[3]);
+        cswap(h.t[1], h.ref[1], h.t[2], h.ref[2]);
+        if (h.t[3] < inf) sstack_push(saddr, ovf, sp, h.ref[3], h.t[3]);
+        if (h.t[2] < inf) sstack_push(saddr, ovf, sp, h.ref[2], h.t[2]);
+        sstack_push(saddr, ovf, sp, h.ref[1], h.t[1]);
+        return h.ref[0];
+    }
+    const int c = __ffs(mask) - 1;
+    return c == 0 ? h.ref[0] : (c == 1 ? h.ref[1] : (c == 2 ? h.ref[2] : h.ref[3]));
+}
 
 }  // namespace prt

@@ -41,11 +41,13 @@ struct BuildBuffers {
     unsigned int* flags = nullptr;  // [N-1]
     int* scene_box = nullptr;       // 6 ordered ints
     unsigned int* max_depth = nullptr;
+    int* queue = nullptr;           // emit: binary node of each wide record
+    unsigned int* tails = nullptr;  // emit: queue tail, triangle tail
     void free_all() {
         cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
         cudaFree(cub_tmp); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(bmin);
         cudaFree(bmax); cudaFree(tcount); cudaFree(icount); cudaFree(collapsed); cudaFree(flags);
-        cudaFree(scene_box); cudaFree(max_depth);
+        cudaFree(scene_box); cudaFree(max_depth); cudaFree(queue); cudaFree(tails);
     }
 };
 
@@ -291,79 +293,116 @@ __device__ __forceinline__ void write_leaf_tris(const float4* __restrict__ verts
     }
 }
 
-__global__ void emit_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vals,
-                            const int* __restrict__ left, const int* __restrict__ right,
-                            const int* __restrict__ parent, const float4* __restrict__ bmin,
-                            const float4* __restrict__ bmax, const uint32_t* __restrict__ tcount,
-                            const uint32_t* __restrict__ icount, const uint8_t* __restrict__ collapsed,
-                            int n, Node32* nodes, float4* tris_out, unsigned int* max_depth) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    if (collapsed[i]) return;
-    uint32_t idx = 0, tstart = 0, depth = 0;
-    for (int c = i; c != 0;) {
-        int p = parent[c];
-        if (collapsed[p]) return;
-        int lp = left[p];
-        if (c != lp) { idx += 1 + icount[lp]; tstart += tcount[lp]; }
-        else idx += 1;
-        c = p;
-        ++depth;
-    }
-    atomicMax(max_depth, depth + 1);
-    int l = left[i], r = right[i];
-    bool lleaf = l >= n - 1 || collapsed[l], rleaf = r >= n - 1 || collapsed[r];
-    uint32_t c0 = lleaf ? tcount[l] : 0u, c1 = rleaf ? tcount[r] : 0u;
-    float4 lo4 = bmin[i], hi4 = bmax[i];
-    float4 llo = bmin[l], lhi = bmax[l], rlo = bmin[r], rhi = bmax[r];
-    float o[3] = {lo4.x, lo4.y, lo4.z};
-    float ext[3] = {hi4.x - lo4.x, hi4.y - lo4.y, hi4.z - lo4.z};
-    float clo[2][3] = {{llo.x, llo.y, llo.z}, {rlo.x, rlo.y, rlo.z}};
-    float chi[2][3] = {{lhi.x, lhi.y, lhi.z}, {rhi.x, rhi.y, rhi.z}};
-    uint32_t e[3], q[2][2][3];
+// ---- emit: collapse the binary tree into 4-wide records, breadth first ---------------------
+// queue[i] = binary node that becomes wide record i.  One launch per level: a thread takes one
+// record, widens {left, right} by (at most twice) replacing the internal child of largest
+// surface area with its two children, quantises the child boxes in the record's frame, appends
+// internal children to the queue (their queue position IS their record index) and copies the
+// triangles of leaf children to a freshly reserved contiguous range.
+struct EmitArgs {
+    const float4* verts;
+    const uint32_t* vals;
+    const int* left;
+    const int* right;
+    const float4* bmin;
+    const float4* bmax;
+    const uint32_t* tcount;
+    const uint8_t* collapsed;
+    int n;
+    int* queue;
+    unsigned int* queue_tail;
+    unsigned int* tri_tail;
+    Node64* nodes;
+    float4* tris_out;
+};
+
+__device__ __forceinline__ void write_record(Node64* out, const float o[3], const float ext[3],
+                                             const float clo[4][3], const float chi[4][3],
+                                             const uint32_t ref[4], int nc) {
+    uint32_t e[3], qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
     for (int a = 0; a < 3; ++a) {
         e[a] = quant_axis_exp(ext[a]);
         while (true) {
-            float scale = __uint_as_float(e[a] << 23);
-            bool ok = quant_planes(o[a], scale, clo[0][a], chi[0][a], q[0][0][a], q[0][1][a]);
-            ok = quant_planes(o[a], scale, clo[1][a], chi[1][a], q[1][0][a], q[1][1][a]) && ok;
+            const float scale = __uint_as_float(e[a] << 23);
+            bool ok = true;
+            uint32_t wl = 0, wh = 0;
+            for (int c = 0; c < 4; ++c) {
+                uint32_t l = 255u, h = 0u;  // absent child: inverted planes (and ref == kNoChild)
+                if (c < nc) ok = quant_planes(o[a], scale, clo[c][a], chi[c][a], l, h) && ok;
+                wl |= l << (8 * c);
+                wh |= h << (8 * c);
+            }
+            qlo[a] = wl; qhi[a] = wh;
             if (ok || e[a] >= 254) break;
             ++e[a];
         }
     }
-    Node32 nd;
-    nd.ox = o[0]; nd.oy = o[1]; nd.oz = o[2];
-    nd.em = e[0] | (e[1] << 8) | (e[2] << 16) | (c0 << 24) | (c1 << 28);
-    // one word per axis: child0.lo | child0.hi << 8 | child1.lo << 16 | child1.hi << 24
-    nd.q0 = q[0][0][0] | (q[0][1][0] << 8) | (q[1][0][0] << 16) | (q[1][1][0] << 24);
-    nd.q1 = q[0][0][1] | (q[0][1][1] << 8) | (q[1][0][1] << 16) | (q[1][1][1] << 24);
-    nd.q2 = q[0][0][2] | (q[0][1][2] << 8) | (q[1][0][2] << 16) | (q[1][1][2] << 24);
-    if (!lleaf && !rleaf) nd.link = idx + 1 + icount[l];
-    else if (lleaf) nd.link = tstart;
-    else nd.link = tstart + tcount[l];
-    nodes[idx] = nd;
-    if (lleaf) write_leaf_tris(verts, vals, left, right, n, l, tstart, tris_out);
-    if (rleaf) write_leaf_tris(verts, vals, left, right, n, r, tstart + tcount[l], tris_out);
+    uint4* p = reinterpret_cast<uint4*>(out);
+    p[0] = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), e[0] | (e[1] << 8) | (e[2] << 16));
+    p[1] = make_uint4(qlo[0], qhi[0], qlo[1], qhi[1]);
+    p[2] = make_uint4(qlo[2], qhi[2], ref[0], ref[1]);
+    p[3] = make_uint4(ref[2], ref[3], 0u, 0u);
 }
 
-// n == 1: a single record whose child0 is the only triangle and child1 is absent
-__global__ void emit_single_kernel(const float4* __restrict__ verts, Node32* nodes, float4* tris_out) {
+__global__ void emit4_kernel(EmitArgs A, unsigned int level_begin, unsigned int level_end) {
+    const unsigned int idx = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= level_end) return;
+    const int n = A.n;
+    const int v = A.queue[idx];
+    int ch[4];
+    int nc = 2;
+    ch[0] = A.left[v];
+    ch[1] = A.right[v];
+    for (int it = 0; it < 2; ++it) {
+        int best = -1;
+        float ba = -1.0f;
+        for (int k = 0; k < nc; ++k) {
+            const int c = ch[k];
+            if (c < n - 1 && !A.collapsed[c]) {
+                const float sa = A.bmax[c].w;
+                if (sa > ba) { ba = sa; best = k; }
+            }
+        }
+        if (best < 0) break;
+        const int c = ch[best];
+        ch[best] = A.left[c];
+        ch[nc++] = A.right[c];
+    }
+    const float4 lo4 = A.bmin[v], hi4 = A.bmax[v];
+    const float o[3] = {lo4.x, lo4.y, lo4.z};
+    const float ext[3] = {hi4.x - lo4.x, hi4.y - lo4.y, hi4.z - lo4.z};
+    float clo[4][3], chi[4][3];
+    uint32_t ref[4] = {kNoChild, kNoChild, kNoChild, kNoChild};
+    for (int k = 0; k < nc; ++k) {
+        const int c = ch[k];
+        const float4 l = A.bmin[c], h = A.bmax[c];
+        clo[k][0] = l.x; clo[k][1] = l.y; clo[k][2] = l.z;
+        chi[k][0] = h.x; chi[k][1] = h.y; chi[k][2] = h.z;
+        if (c >= n - 1 || A.collapsed[c]) {
+            const uint32_t cnt = A.tcount[c];
+            const uint32_t start = atomicAdd(A.tri_tail, cnt);
+            write_leaf_tris(A.verts, A.vals, A.left, A.right, n, c, start, A.tris_out);
+            ref[k] = kLeafFlag | (start << 3) | cnt;
+        } else {
+            const unsigned int pos = atomicAdd(A.queue_tail, 1u);
+            A.queue[pos] = c;
+            ref[k] = pos;
+        }
+    }
+    write_record(A.nodes + idx, o, ext, clo, chi, ref, nc);
+}
+
+// n == 1: one record whose only child is the only triangle
+__global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nodes, float4* tris_out) {
     float3 lo, hi;
     tri_box(verts, 0, lo, hi);
-    float o[3] = {lo.x, lo.y, lo.z}, l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
-    uint32_t e[3], ql[3], qh[3];
-    for (int a = 0; a < 3; ++a) {
-        e[a] = quant_axis_exp(h3[a] - l3[a]);
-        while (!quant_planes(o[a], __uint_as_float(e[a] << 23), l3[a], h3[a], ql[a], qh[a]) && e[a] < 254) ++e[a];
-    }
-    Node32 nd;
-    nd.ox = o[0]; nd.oy = o[1]; nd.oz = o[2];
-    nd.em = e[0] | (e[1] << 8) | (e[2] << 16) | (1u << 24) | (0xFu << 28);
-    nd.q0 = ql[0] | (qh[0] << 8);
-    nd.q1 = ql[1] | (qh[1] << 8);
-    nd.q2 = ql[2] | (qh[2] << 8);
-    nd.link = 0;
-    nodes[0] = nd;
+    const float o[3] = {lo.x, lo.y, lo.z};
+    const float ext[3] = {hi.x - lo.x, hi.y - lo.y, hi.z - lo.z};
+    float clo[4][3], chi[4][3];
+    clo[0][0] = lo.x; clo[0][1] = lo.y; clo[0][2] = lo.z;
+    chi[0][0] = hi.x; chi[0][1] = hi.y; chi[0][2] = hi.z;
+    const uint32_t ref[4] = {kLeafFlag | 1u, kNoChild, kNoChild, kNoChild};
+    write_record(nodes, o, ext, clo, chi, ref, 1);
     tris_out[0] = verts[0]; tris_out[1] = verts[1]; tris_out[2] = verts[2];
 }
 
@@ -447,17 +486,42 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         BUILD_TRY(cudaMemcpy(&root_lo, B.bmin, sizeof(float4), cudaMemcpyDeviceToHost));
         BUILD_TRY(cudaMemcpy(&root_hi, B.bmax, sizeof(float4), cudaMemcpyDeviceToHost));
     }
-    BUILD_TRY(cudaMalloc(&ctx->nodes, sizeof(Node32) * (size_t)n_rec));
+    // upper bound on wide records = surviving binary internal nodes; shrunk to fit afterwards
+    Node64* wide = nullptr;
+    BUILD_TRY(cudaMalloc(&wide, sizeof(Node64) * (size_t)n_rec));
+    unsigned int depth = 0, n_wide = 1;
     cudaEventRecord(ev[5]);
-    if (n > 1)
-        emit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[1], B.left, B.right, B.parent, B.bmin, B.bmax,
-                               B.tcount, B.icount, B.collapsed, n, ctx->nodes, ctx->tris_leaf, B.max_depth);
-    else
-        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tris_leaf);
+    if (n > 1) {
+        BUILD_TRY(cudaMalloc(&B.queue, sizeof(int) * (size_t)n_rec));
+        BUILD_TRY(cudaMalloc(&B.tails, 2 * sizeof(unsigned int)));
+        const unsigned int init_tails[2] = {1u, 0u};
+        BUILD_TRY(cudaMemset(B.queue, 0, sizeof(int)));  // record 0 = binary root (node 0)
+        BUILD_TRY(cudaMemcpy(B.tails, init_tails, sizeof init_tails, cudaMemcpyHostToDevice));
+        EmitArgs A;
+        A.verts = ctx->verts_gid; A.vals = B.vals[1]; A.left = B.left; A.right = B.right;
+        A.bmin = B.bmin; A.bmax = B.bmax; A.tcount = B.tcount; A.collapsed = B.collapsed; A.n = n;
+        A.queue = B.queue; A.queue_tail = B.tails; A.tri_tail = B.tails + 1; A.nodes = wide;
+        A.tris_out = ctx->tris_leaf;
+        unsigned int begin = 0, end = 1;
+        while (begin < end) {
+            emit4_kernel<<<(end - begin + T - 1) / T, T>>>(A, begin, end);
+            unsigned int tail = 0;
+            BUILD_TRY(cudaMemcpy(&tail, B.tails, sizeof tail, cudaMemcpyDeviceToHost));
+            begin = end;
+            end = tail;
+            ++depth;
+        }
+        n_wide = end;
+    } else {
+        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, wide, ctx->tris_leaf);
+        depth = 1;
+    }
     cudaEventRecord(ev[6]);
     BUILD_TRY(cudaDeviceSynchronize());
-    unsigned int depth = 0;
-    BUILD_TRY(cudaMemcpy(&depth, B.max_depth, sizeof depth, cudaMemcpyDeviceToHost));
+    BUILD_TRY(cudaMalloc(&ctx->nodes, sizeof(Node64) * (size_t)n_wide));
+    BUILD_TRY(cudaMemcpy(ctx->nodes, wide, sizeof(Node64) * (size_t)n_wide, cudaMemcpyDeviceToDevice));
+    cudaFree(wide);
+    n_rec = n_wide;
     float ms[6];
     for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
     for (auto& e : ev) cudaEventDestroy(e);
@@ -468,7 +532,7 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     st.ms_total = ms[0] + ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
     st.depth = depth;
     B.free_all();
-    if (depth + 2 >= (unsigned)kMaxStack) { *too_deep = true; return PRT_OK; }
+    if (3 * depth + 1 > (unsigned)kMaxStack) { *too_deep = true; return PRT_OK; }  // <= 3 pushes per level
     ctx->n_nodes = n_rec;
     ctx->bvh_built = true;
     ctx->bvh_stats = st;

@@ -8,28 +8,29 @@
 
 namespace prt {
 
-constexpr int kSmemStack = 24;          // per-thread traversal stack entries held in shared memory
 constexpr int kTraceThreads = 128;      // CTA size of the traversal kernels
 constexpr uint32_t kLeafFlag = 0x80000000u;
+constexpr uint32_t kNoChild = 0xFFFFFFFFu;   // absent child slot; also the "traversal finished" marker
 
 // ---- device scene ---------------------------------------------------------
 // Triangles live in HBM as 3 x float4 (48 B), in BVH leaf (DFS) order so that a
 // leaf's triangles are contiguous:  (p0.xyz, bits(global id)), (p1.xyz,
 // bits(material)), (p2.xyz, 0).  Shading data (normal + material) is a separate
 // float4 array indexed by the GLOBAL id, touched once per path vertex only.
-struct Node32 {        // 32 B, two float4 / one sector
-    float ox, oy, oz;  // frame origin
-    uint32_t em;       // ex | ey<<8 | ez<<16 | meta<<24   (scale = 2^(e-127)); meta: cnt0 | cnt1<<4
-    uint32_t q0;       // x planes: child0.lo, child0.hi, child1.lo, child1.hi (one byte each)
-    uint32_t q1;       // y planes, same order
-    uint32_t q2;       // z planes, same order
-    uint32_t link;     // see bvh.cuh
+// 4-wide BVH node, 64 B = four float4 = two 32-byte sectors: 16 B per child box + reference,
+// the same bytes-per-child as a 32-byte 2-wide node (see DESIGN.md 2 for why 4-wide).
+struct Node64 {
+    float ox, oy, oz;   // frame origin (node box min)
+    uint32_t em;        // ex | ey<<8 | ez<<16 : plane = o + q * 2^(e-127)
+    uint32_t qx_lo, qx_hi, qy_lo, qy_hi;  // byte c = child c : quantised lo / hi planes per axis
+    uint32_t qz_lo, qz_hi, ref0, ref1;    // child refs: record index, or kLeafFlag | first_tri<<3 | count,
+    uint32_t ref2, ref3, pad0, pad1;      // or kNoChild
 };
-static_assert(sizeof(Node32) == 32, "node must be 32 bytes");
+static_assert(sizeof(Node64) == 64, "node must be 64 bytes");
 
 struct SceneDev {
     const float4* tris;      // [nt*3] leaf order
-    const Node32* nodes;     // [n_nodes]
+    const Node64* nodes;     // [n_nodes]
     const float4* shade;     // [nt] by global id: normal.xyz, bits(material)
     const prt_material* mats;
     const uint32_t* light_tris;  // global ids

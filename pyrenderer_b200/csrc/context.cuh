@@ -21,7 +21,7 @@ struct prt_ctx {
 
     // BVH (device)
     float4* tris_leaf = nullptr;   // [nt*3] leaf order, w carries gid / material
-    prt::Node32* nodes = nullptr;
+    prt::Node64* nodes = nullptr;
     uint32_t n_nodes = 0;
     bool bvh_built = false;
     prt_bvh_stats bvh_stats = {};

@@ -26,43 +26,6 @@ namespace prt {
 // scheduling knobs live in SceneDev (refill_idle: refill when at least this many lanes are idle;
 // leaf_batch: intersect leaves when at least this many lanes are parked); defaults in context.cuh,
 // overridable with PRT_REFILL_IDLE / PRT_LEAF_BATCH for tuning sweeps.
-constexpr uint32_t kDone = 0xFFFFFFFFu;  // has kLeafFlag set
-
-// Per-lane stack of (child reference, entry distance) pairs: kPStack levels in shared
-// memory ([level][lane] of 8-byte slots, conflict-free), deeper levels in local memory.
-// Keeping the entry distance lets a pop discard, without touching memory, every
-// subtree that a closer hit found in the meantime has made irrelevant.
-constexpr int kPStack = 16;
-constexpr int kPStackOvf = kMaxStack - kPStack;
-
-__device__ __forceinline__ void sstack_push(uint32_t saddr, uint2* ovf, int& sp, uint32_t ref, float t) {
-    if (sp < kPStack)
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)), "r"(ref), "r"(__float_as_uint(t)) : "memory");
-    else
-        ovf[sp - kPStack] = make_uint2(ref, __float_as_uint(t));
-    ++sp;
-}
-__device__ __forceinline__ uint32_t sstack_pop(uint32_t saddr, const uint2* ovf, int& sp, float& t) {
-    --sp;
-    uint32_t ref, tb;
-    if (sp < kPStack) {
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)) : "memory");
-    } else {
-        uint2 e = ovf[sp - kPStack];
-        ref = e.x; tb = e.y;
-    }
-    t = __uint_as_float(tb);
-    return ref;
-}
-// pop until an entry that can still beat `bound` (or the stack is empty -> kDone)
-__device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, const uint2* ovf, int& sp, float bound) {
-    while (sp > 0) {
-        float t;
-        const uint32_t ref = sstack_pop(saddr, ovf, sp, t);
-        if (t <= bound) return ref;
-    }
-    return 0xFFFFFFFFu;
-}
 
 template <int MODE, bool COUNT, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsigned int* fetch,
@@ -126,27 +89,11 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep)
         if (has_ray && !(cur & kLeafFlag)) {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
             if (COUNT) ++c_nodes;
-            float t0, t1;
-            const int m = node_test<false>(n0, n1, rb, tmin, MODE == MODE_CLOSEST ? bt : tmax, t0, t1);
-            // child references, branch-free (layout: bvh.cuh header)
-            const uint32_t em = __float_as_uint(n0.w), link = __float_as_uint(n1.w);
-            const uint32_t c0 = (em >> 24) & 0xFu, c1 = em >> 28;
-            const uint32_t leaf0 = kLeafFlag | (link << 3) | c0;
-            const uint32_t leaf1 = kLeafFlag | ((link + c0) << 3) | c1;  // c0 == 0 when child0 is internal
-            const uint32_t r0 = c0 ? leaf0 : cur + 1;
-            const uint32_t r1 = c1 ? leaf1 : (c0 ? cur + 1 : link);
-            if (m == 3) {
-                const bool swap = MODE == MODE_CLOSEST && t1 < t0;
-                sstack_push(saddr, ovf, sp, swap ? r0 : r1, swap ? t0 : t1);
-                cur = swap ? r1 : r0;
-            } else if (m) {
-                cur = (m & 1) ? r0 : r1;
-            } else {
-                cur = sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? bt : tmax);
-            }
+            NodeHits h;
+            const float bound = MODE == MODE_CLOSEST ? bt : tmax;
+            const int m = node_test4<false>(sc.nodes + cur, rb, tmin, bound, h);
+            cur = descend(m, h, saddr, ovf, sp, bound);
         }
 
         // ---- leaves: parked lanes go together

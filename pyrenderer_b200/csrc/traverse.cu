@@ -15,7 +15,7 @@ template <int MODE, bool EXACT, bool COUNT, bool BRUTE>
 __global__ void __launch_bounds__(kTraceThreads)
 trace_kernel(SceneDev sc, const float4* __restrict__ rays, uint64_t n, void* out0, void* out1,
              uint32_t* flag_list, unsigned int* flag_count, Counters* ctr) {
-    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    __shared__ uint2 s_stack[kPStack][kTraceThreads];
     uint64_t i = (uint64_t)blockIdx.x * kTraceThreads + threadIdx.x;
     TraceResult res;
     res.n_nodes = 0; res.n_tris = 0;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kTraceThreads)
 resolve_kernel(SceneDev sc, const float4* __restrict__ rays, void* out0, void* out1,
                const uint32_t* __restrict__ flag_list, const unsigned int* __restrict__ flag_count,
                Counters* ctr) {
-    __shared__ uint32_t s_stack[kSmemStack][kTraceThreads];
+    __shared__ uint2 s_stack[kPStack][kTraceThreads];
     unsigned int nf = *flag_count;
     for (unsigned int k = blockIdx.x * kTraceThreads + threadIdx.x; k < nf;
          k += gridDim.x * kTraceThreads) {

@@ -48,17 +48,17 @@ __device__ __forceinline__ bool process_tris(const SceneDev& sc, const RayW& rw,
     return false;
 }
 
-// FP32 traversal.  `stack_smem` = &s_stack[0][threadIdx.x].
+// FP32 traversal, one ray per thread.  `stack_col` = &s_stack[0][threadIdx.x] of a
+// __shared__ uint2 s_stack[kPStack][kTraceThreads].
 template <int MODE, bool EXACT, bool COUNT, bool BRUTE>
 __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 rd,
-                                          uint32_t* stack_smem, TraceResult& res) {
+                                          uint2* stack_col, TraceResult& res) {
     float3 o = xyz(ro), d = xyz(rd);
     float tmin = ro.w, tmax = rd.w;
     res.t = tmax; res.u = 0.f; res.v = 0.f; res.dt = 0.f; res.gid = -1;
     res.uncertain = false; res.count = 0; res.sum = 0ull; res.n_nodes = 0; res.n_tris = 0;
     RayW rw = make_rayw(o, d);
     if (BRUTE) {
-        // 7-bit leaf counts do not apply: walk the whole triangle array
         for (uint32_t s = 0; s < sc.nt; s += 4096u) {
             uint32_t c = min(4096u, sc.nt - s);
             if (process_tris<MODE, EXACT, COUNT>(sc, rw, s, c, tmin, tmax, res)) return;
@@ -67,36 +67,23 @@ __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 
     }
     if (sc.n_nodes == 0) return;
     RayBox rb = make_raybox(o, d);
-    Stack st;
-    st.smem = stack_smem;
-    st.sp = 0;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
+    uint2 ovf[kPStackOvf];
+    int sp = 0;
     uint32_t cur = 0;
-    while (true) {
+    while (cur != kDone) {
+        // EXACT: a candidate closer than best + its error bound must still be visited
+        const float bound = MODE == MODE_CLOSEST ? res.t + (EXACT ? res.dt : 0.0f) : tmax;
         if (!(cur & kLeafFlag)) {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1);
             if (COUNT) ++res.n_nodes;
-            float t0, t1;
-            float far = MODE == MODE_CLOSEST ? res.t + (EXACT ? res.dt : 0.0f) : tmax;
-            int m = node_test<EXACT>(n0, n1, rb, tmin, far, t0, t1);
-            if (m) {
-                uint32_t r0, r1;
-                node_refs(cur, __float_as_uint(n0.w), __float_as_uint(n1.w), r0, r1);
-                if (m == 3) {
-                    bool swap = MODE == MODE_CLOSEST && t1 < t0;
-                    st.push(swap ? r0 : r1);
-                    cur = swap ? r1 : r0;
-                } else {
-                    cur = (m & 1) ? r0 : r1;
-                }
-                continue;
-            }
+            NodeHits h;
+            const int m = node_test4<EXACT>(sc.nodes + cur, rb, tmin, bound, h);
+            cur = descend(m, h, saddr, ovf, sp, bound);
         } else {
             uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
             if (process_tris<MODE, EXACT, COUNT>(sc, rw, start, cnt, tmin, tmax, res)) return;
+            cur = sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? res.t + (EXACT ? res.dt : 0.0f) : tmax);
         }
-        if (st.sp == 0) break;
-        cur = st.pop();
     }
 }
 
@@ -137,7 +124,7 @@ __device__ __forceinline__ bool process_tris64(const SceneDev& sc, const double*
 
 template <int MODE, bool BRUTE>
 __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, float4 rd,
-                                              uint32_t* stack_smem, TraceResult64& res) {
+                                              uint2* stack_col, TraceResult64& res) {
     double o[3] = {(double)ro.x, (double)ro.y, (double)ro.z};
     double d[3] = {(double)rd.x, (double)rd.y, (double)rd.z};
     double tmin = (double)ro.w, tmax = (double)rd.w;
@@ -151,36 +138,22 @@ __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, flo
     }
     if (sc.n_nodes == 0) return;
     RayBox rb = make_raybox(xyz(ro), xyz(rd));
-    Stack st;
-    st.smem = stack_smem;
-    st.sp = 0;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
+    uint2 ovf[kPStackOvf];
+    int sp = 0;
     uint32_t cur = 0;
-    while (true) {
+    while (cur != kDone) {
+        // box culling stays FP32 but conservative: bound rounded up, intervals widened (EXACT)
+        const float bound = MODE == MODE_CLOSEST ? __double2float_ru(res.t) : rd.w;
         if (!(cur & kLeafFlag)) {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1);
-            float t0, t1;
-            float far = MODE == MODE_CLOSEST ? __double2float_ru(res.t) : rd.w;
-            // widen the near side too: tmin enters the slab as a float rounded towards -inf
-            int m = node_test<true>(n0, n1, rb, ro.w, far, t0, t1);
-            if (m) {
-                uint32_t r0, r1;
-                node_refs(cur, __float_as_uint(n0.w), __float_as_uint(n1.w), r0, r1);
-                if (m == 3) {
-                    bool swap = MODE == MODE_CLOSEST && t1 < t0;
-                    st.push(swap ? r0 : r1);
-                    cur = swap ? r1 : r0;
-                } else {
-                    cur = (m & 1) ? r0 : r1;
-                }
-                continue;
-            }
+            NodeHits h;
+            const int m = node_test4<true>(sc.nodes + cur, rb, ro.w, bound, h);
+            cur = descend(m, h, saddr, ovf, sp, bound);
         } else {
             uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
             if (process_tris64<MODE>(sc, o, d, start, cnt, tmin, tmax, res)) return;
+            cur = sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? __double2float_ru(res.t) : rd.w);
         }
-        if (st.sp == 0) break;
-        cur = st.pop();
     }
 }
 
