@@ -98,6 +98,7 @@ typedef struct {
 
 typedef struct {
     uint32_t n_tris, n_nodes, depth, max_leaf_tris;
+    uint32_t morton_sorted; /* 1 if the radix sort left the Morton keys in order (self-check) */
     float sah_cost;
     float ms_total, ms_morton, ms_sort, ms_hierarchy, ms_refit, ms_emit;
 } prt_bvh_stats;

@@ -72,8 +72,8 @@ def main():
             print(f"render refill_idle {ri:2d} leaf_batch {lb:2d}: {best:7.2f} ms / 8 spp  {(c['rays_closest'] + c['rays_shadow']) / best / 1e3:8.1f} Mrays/s", flush=True)
             ctx.close()
     else:
-        for ri in (2, 4, 6, 8, 12, 16):
-            for lb in (1, 4, 6, 8, 12, 16):
+        for ri in (4, 6, 8, 12):
+            for lb in (4, 8, 12, 16, 20, 24):
                 os.environ["PRT_REFILL_IDLE"] = str(ri); os.environ["PRT_LEAF_BATCH"] = str(lb)
                 ctx = _abi.Context(0)
                 ctx.set_triangles_dev(tris, 1_000_000); ctx.build_bvh()

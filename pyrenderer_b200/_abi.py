@@ -37,7 +37,7 @@ class PrtRenderParams(C.Structure):
 
 class PrtBvhStats(C.Structure):
     _fields_ = [("n_tris", C.c_uint32), ("n_nodes", C.c_uint32), ("depth", C.c_uint32),
-                ("max_leaf_tris", C.c_uint32), ("sah_cost", C.c_float), ("ms_total", C.c_float),
+                ("max_leaf_tris", C.c_uint32), ("morton_sorted", C.c_uint32), ("sah_cost", C.c_float), ("ms_total", C.c_float),
                 ("ms_morton", C.c_float), ("ms_sort", C.c_float), ("ms_hierarchy", C.c_float),
                 ("ms_refit", C.c_float), ("ms_emit", C.c_float)]
 
@@ -210,9 +210,13 @@ class Context:
         self._check(self.lib.prt_trace_all(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(counts_dev),
                                            _dev_ptr(sums_dev), int(flags), _stream_ptr(stream)))
 
-    def trace_closest_host(self, rays, flags=0):
+    def trace_closest_host(self, rays, flags=0, out=None):
+        """``out``: optional HIT_DTYPE array to receive the hits (page-locked for speed)."""
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
-        if rays.shape[0] >= (1 << 16):  # big batches: page-locked result buffer (async D2H)
+        if out is not None:
+            hits = out
+            assert hits.dtype == HIT_DTYPE and hits.shape[0] == rays.shape[0] and hits.flags.c_contiguous
+        elif rays.shape[0] >= (1 << 16):  # big batches: page-locked result buffer (async D2H)
             import torch
             hits = torch.empty((rays.shape[0], 4), dtype=torch.float32, pin_memory=True).numpy()
             hits = hits.view(HIT_DTYPE).reshape(rays.shape[0])

@@ -127,27 +127,24 @@ __device__ __forceinline__ void cswap(float& ta, uint32_t& ra, float& tb, uint32
 }
 
 // Continue after a node visit: the nearest hit child becomes the next reference, the others
-// are pushed far-first (so the nearer ones pop first); no hit -> pop.
+// are pushed far-first (so the nearer ones pop first); no hit -> pop.  Written without
+// data-dependent branches around the sorting network: in a warp the lanes have 0..4 hits
+// each, and serialising three code paths costs more than sorting unconditionally.
 __device__ __forceinline__ uint32_t descend(int mask, NodeHits& h, uint32_t saddr, uint2* ovf, int& sp,
                                             float bound) {
-    if (mask == 0) return sstack_pop_live(saddr, ovf, sp, bound);
     const float inf = __int_as_float(0x7f800000);
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        if (!(mask & (1 << c))) h.t[c] = inf;
-    if (mask & (mask - 1)) {  // two or more hits: sorting network for 4 (misses sort to the back)
-        cswap(h.t[0], h.ref[0], h.t[1], h.ref[1]);
-        cswap(h.t[2], h.ref[2], h.t[3], h.ref[3]);
-        cswap(h.t[0], h.ref[0], h.t[2], h.ref[2]);
-        cswap(h.t[1], h.ref[1], h.t[3], h.ref[3]);
-        cswap(h.t[1], h.ref[1], h.t[2], h.ref[2]);
-        if (h.t[3] < inf) sstack_push(saddr, ovf, sp, h.ref[3], h.t[3]);
-        if (h.t[2] < inf) sstack_push(saddr, ovf, sp, h.ref[2], h.t[2]);
-        sstack_push(saddr, ovf, sp, h.ref[1], h.t[1]);
-        return h.ref[0];
-    }
-    const int c = __ffs(mask) - 1;
-    return c == 0 ? h.ref[0] : (c == 1 ? h.ref[1] : (c == 2 ? h.ref[2] : h.ref[3]));
+    for (int c = 0; c < 4; ++c) h.t[c] = (mask & (1 << c)) ? h.t[c] : inf;
+    cswap(h.t[0], h.ref[0], h.t[1], h.ref[1]);  // sorting network for 4; misses sort to the back
+    cswap(h.t[2], h.ref[2], h.t[3], h.ref[3]);
+    cswap(h.t[0], h.ref[0], h.t[2], h.ref[2]);
+    cswap(h.t[1], h.ref[1], h.t[3], h.ref[3]);
+    cswap(h.t[1], h.ref[1], h.t[2], h.ref[2]);
+    if (h.t[3] < inf) sstack_push(saddr, ovf, sp, h.ref[3], h.t[3]);
+    if (h.t[2] < inf) sstack_push(saddr, ovf, sp, h.ref[2], h.t[2]);
+    if (h.t[1] < inf) sstack_push(saddr, ovf, sp, h.ref[1], h.t[1]);
+    if (mask == 0) return sstack_pop_live(saddr, ovf, sp, bound);
+    return h.ref[0];
 }
 
 }  // namespace prt

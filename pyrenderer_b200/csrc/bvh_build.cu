@@ -1,25 +1,25 @@
-// bvh_build.cu -- GPU LBVH build emitting the 32-byte quantised node layout.
+// bvh_build.cu -- GPU LBVH build emitting the quantised 4-wide node layout (Node64).
 //
-// Pipeline (all on the device, no host round trips except the final sizes):
-//   1. bounds_kernel     scene AABB (block reduce + ordered-int atomics)
+// Pipeline (all on the device; the host only reads a queue length per tree level):
+//   1. bounds_kernel     scene AABB (warp reduce + ordered-int atomics)
 //   2. morton_kernel     30-bit Morton code of each triangle's box centre
-//   3. radix sort        (key, triangle) pairs, cub::DeviceRadixSort
+//   3. radix sort        (key, triangle) pairs, 4 x 8-bit stable LSD passes (radix_sort.cuh)
 //   4. hierarchy_kernel  Karras 2012 "Maximizing parallelism in the construction
 //                        of BVHs, octrees and k-d trees": one thread per internal node
 //   5. refit_kernel      bottom-up with arrival flags: boxes, SAH cost, SAH tree
 //                        rotations (3-leaf treelets) and SAH leaf collapse (<= 7 tris)
-//   6. emit_kernel       DFS pre-order record index + DFS triangle offset per surviving
-//                        node (walk to the root), conservative 8-bit quantisation,
-//                        triangles rewritten in leaf order
+//   6. emit4_kernel      breadth-first collapse of the binary tree into 4-wide records
+//                        (expand the child of largest surface area), conservative 8-bit
+//                        quantisation of the child boxes in the record's frame, leaf
+//                        triangles copied to contiguous ranges
 //
 // Replaces: BVH.build / build_helper / sah_heuristic accelerators/bvh.py:70-215
 // (recursive binned SAH on the CPU), Aggregator.update accelerators/aggregator.py:25-55
 // (flat soup for zero-thickness primitives: no special path here, flat boxes
 // quantise fine) and BVH.build accelerators/bvh_taichi.py:126-161.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "context.cuh"
 #include "bvh.cuh"
+#include "radix_sort.cuh"
 
 namespace prt {
 
@@ -28,8 +28,7 @@ namespace {
 struct BuildBuffers {
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
-    void* cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    void* sort_tmp = nullptr;
     int* left = nullptr;     // [N-1]
     int* right = nullptr;    // [N-1]
     int* parent = nullptr;   // [2N-1]
@@ -45,7 +44,7 @@ struct BuildBuffers {
     unsigned int* tails = nullptr;  // emit: queue tail, triangle tail
     void free_all() {
         cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
-        cudaFree(cub_tmp); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(bmin);
+        cudaFree(sort_tmp); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(bmin);
         cudaFree(bmax); cudaFree(tcount); cudaFree(icount); cudaFree(collapsed); cudaFree(flags);
         cudaFree(scene_box); cudaFree(max_depth); cudaFree(queue); cudaFree(tails);
     }
@@ -119,6 +118,12 @@ __device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, i
     uint32_t a = keys[i], b = keys[j];
     if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
     return __clz(a ^ b);
+}
+
+// sortedness self-check of the radix sort (counts inversions; reported in prt_bvh_stats)
+__global__ void check_sorted_kernel(const uint32_t* __restrict__ keys, uint32_t n, unsigned int* bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && keys[i] > keys[i + 1]) atomicAdd(bad, 1u);
 }
 
 // node ids: internal i -> i (0..n-2), leaf j -> (n-1)+j
@@ -344,9 +349,16 @@ __device__ __forceinline__ void write_record(Node64* out, const float o[3], cons
     p[3] = make_uint4(ref[2], ref[3], 0u, 0u);
 }
 
-__global__ void emit4_kernel(EmitArgs A, unsigned int level_begin, unsigned int level_end) {
-    const unsigned int idx = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= level_end) return;
+// level[0] = begin, level[1] = end of the current level in the queue, level[2] = depth so far
+__global__ void emit_advance_kernel(unsigned int* level, const unsigned int* queue_tail) {
+    level[0] = level[1];
+    level[1] = *queue_tail;
+    if (level[0] < level[1]) ++level[2];
+}
+
+__global__ void emit4_kernel(EmitArgs A, const unsigned int* __restrict__ level) {
+    const unsigned int idx = level[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= level[1]) return;
     const int n = A.n;
     const int v = A.queue[idx];
     int ch[4];
@@ -373,20 +385,31 @@ __global__ void emit4_kernel(EmitArgs A, unsigned int level_begin, unsigned int 
     const float ext[3] = {hi4.x - lo4.x, hi4.y - lo4.y, hi4.z - lo4.z};
     float clo[4][3], chi[4][3];
     uint32_t ref[4] = {kNoChild, kNoChild, kNoChild, kNoChild};
+    // siblings get adjacent record slots and adjacent triangle ranges (one reservation each):
+    // a ray that enters two children of this record finds the second one in the same lines
+    uint32_t n_int = 0, n_tri = 0;
+    bool leaf[4];
+    for (int k = 0; k < nc; ++k) {
+        const int c = ch[k];
+        leaf[k] = c >= n - 1 || A.collapsed[c];
+        if (leaf[k]) n_tri += A.tcount[c];
+        else ++n_int;
+    }
+    uint32_t pos = n_int ? atomicAdd(A.queue_tail, n_int) : 0u;
+    uint32_t start = n_tri ? atomicAdd(A.tri_tail, n_tri) : 0u;
     for (int k = 0; k < nc; ++k) {
         const int c = ch[k];
         const float4 l = A.bmin[c], h = A.bmax[c];
         clo[k][0] = l.x; clo[k][1] = l.y; clo[k][2] = l.z;
         chi[k][0] = h.x; chi[k][1] = h.y; chi[k][2] = h.z;
-        if (c >= n - 1 || A.collapsed[c]) {
+        if (leaf[k]) {
             const uint32_t cnt = A.tcount[c];
-            const uint32_t start = atomicAdd(A.tri_tail, cnt);
             write_leaf_tris(A.verts, A.vals, A.left, A.right, n, c, start, A.tris_out);
             ref[k] = kLeafFlag | (start << 3) | cnt;
+            start += cnt;
         } else {
-            const unsigned int pos = atomicAdd(A.queue_tail, 1u);
             A.queue[pos] = c;
-            ref[k] = pos;
+            ref[k] = pos++;
         }
     }
     write_record(A.nodes + idx, o, ext, clo, chi, ref, nc);
@@ -447,8 +470,11 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         BUILD_TRY(cudaMalloc(&B.keys[k], sizeof(uint32_t) * nt));
         BUILD_TRY(cudaMalloc(&B.vals[k], sizeof(uint32_t) * nt));
     }
-    BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, B.cub_bytes, B.keys[0], B.keys[1], B.vals[0], B.vals[1], n, 0, 30));
-    BUILD_TRY(cudaMalloc(&B.cub_tmp, B.cub_bytes ? B.cub_bytes : 16));
+    BUILD_TRY(cudaMalloc(&B.sort_tmp, radix_sort_temp_bytes(nt)));
+    // emit-stage buffers are allocated here too: cudaMalloc inside the timed phases costs milliseconds
+    BUILD_TRY(cudaMalloc(&B.queue, sizeof(int) * (size_t)nt));
+    BUILD_TRY(cudaMalloc(&B.tails, 5 * sizeof(unsigned int)));
+    BUILD_TRY(cudaMalloc(&ctx->nodes, sizeof(Node64) * (size_t)nt));  // upper bound; trimmed below
     BUILD_TRY(cudaMalloc(&B.left, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
     BUILD_TRY(cudaMalloc(&B.right, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
     BUILD_TRY(cudaMalloc(&B.parent, sizeof(int) * nn));
@@ -468,14 +494,15 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     bounds_kernel<<<min(gN, (unsigned)ctx->num_sms * 8u), T>>>(ctx->verts_gid, nt, B.scene_box);
     morton_kernel<<<gN, T>>>(ctx->verts_gid, nt, B.scene_box, B.keys[0], B.vals[0]);
     cudaEventRecord(ev[1]);
-    BUILD_TRY(cub::DeviceRadixSort::SortPairs(B.cub_tmp, B.cub_bytes, B.keys[0], B.keys[1], B.vals[0], B.vals[1], n, 0, 30));
+    const int sorted = radix_sort_pairs(B.keys, B.vals, nt, 30, B.sort_tmp, 0);  // result in keys/vals[sorted]
+    check_sorted_kernel<<<gN, T>>>(B.keys[sorted], nt, B.max_depth);  // max_depth doubles as the inversion counter
     cudaEventRecord(ev[2]);
-    if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[1], n, B.left, B.right, B.parent);
+    if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[sorted], n, B.left, B.right, B.parent);
     cudaEventRecord(ev[3]);
     RefitParams P;
     P.n = n; P.max_leaf = opt.max_leaf_tris; P.cn = opt.cost_node; P.ct = opt.cost_tri;
     P.rotations = (int)opt.rotations;
-    refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[1], B.left, B.right, B.parent, B.bmin, B.bmax,
+    refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[sorted], B.left, B.right, B.parent, B.bmin, B.bmax,
                             B.tcount, B.icount, B.collapsed, B.flags, P);
     cudaEventRecord(ev[4]);
     BUILD_TRY(cudaGetLastError());
@@ -486,41 +513,46 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         BUILD_TRY(cudaMemcpy(&root_lo, B.bmin, sizeof(float4), cudaMemcpyDeviceToHost));
         BUILD_TRY(cudaMemcpy(&root_hi, B.bmax, sizeof(float4), cudaMemcpyDeviceToHost));
     }
-    // upper bound on wide records = surviving binary internal nodes; shrunk to fit afterwards
-    Node64* wide = nullptr;
-    BUILD_TRY(cudaMalloc(&wide, sizeof(Node64) * (size_t)n_rec));
     unsigned int depth = 0, n_wide = 1;
     cudaEventRecord(ev[5]);
     if (n > 1) {
-        BUILD_TRY(cudaMalloc(&B.queue, sizeof(int) * (size_t)n_rec));
-        BUILD_TRY(cudaMalloc(&B.tails, 2 * sizeof(unsigned int)));
-        const unsigned int init_tails[2] = {1u, 0u};
-        BUILD_TRY(cudaMemset(B.queue, 0, sizeof(int)));  // record 0 = binary root (node 0)
-        BUILD_TRY(cudaMemcpy(B.tails, init_tails, sizeof init_tails, cudaMemcpyHostToDevice));
+        const unsigned int init[5] = {1u, 0u, /*level:*/ 0u, 1u, 1u};  // queue tail, tri tail, begin, end, depth
+        BUILD_TRY(cudaMemsetAsync(B.queue, 0, sizeof(int)));  // record 0 = binary root (node 0)
+        BUILD_TRY(cudaMemcpy(B.tails, init, sizeof init, cudaMemcpyHostToDevice));
         EmitArgs A;
-        A.verts = ctx->verts_gid; A.vals = B.vals[1]; A.left = B.left; A.right = B.right;
+        A.verts = ctx->verts_gid; A.vals = B.vals[sorted]; A.left = B.left; A.right = B.right;
         A.bmin = B.bmin; A.bmax = B.bmax; A.tcount = B.tcount; A.collapsed = B.collapsed; A.n = n;
-        A.queue = B.queue; A.queue_tail = B.tails; A.tri_tail = B.tails + 1; A.nodes = wide;
+        A.queue = B.queue; A.queue_tail = B.tails; A.tri_tail = B.tails + 1; A.nodes = ctx->nodes;
         A.tris_out = ctx->tris_leaf;
-        unsigned int begin = 0, end = 1;
-        while (begin < end) {
-            emit4_kernel<<<(end - begin + T - 1) / T, T>>>(A, begin, end);
-            unsigned int tail = 0;
-            BUILD_TRY(cudaMemcpy(&tail, B.tails, sizeof tail, cudaMemcpyDeviceToHost));
-            begin = end;
-            end = tail;
-            ++depth;
+        // One launch per level, driven from the device (no host round trip per level): a level has
+        // at most n_rec records and the tree at most kMaxStack/3 levels that traversal can use.
+        // Levels shrink/grow by <= 4x, so the grid is sized from the previous bound.
+        const int max_levels = kMaxStack / 3 + 1;
+        size_t bound = 1;
+        for (int lv = 0; lv < max_levels; ++lv) {
+            const unsigned g = (unsigned)((bound + T - 1) / T);
+            emit4_kernel<<<g, T>>>(A, B.tails + 2);
+            emit_advance_kernel<<<1, 1>>>(B.tails + 2, B.tails);
+            bound = bound * 4 < (size_t)n_rec ? bound * 4 : (size_t)n_rec;
         }
-        n_wide = end;
+        unsigned int fin[5];
+        BUILD_TRY(cudaMemcpy(fin, B.tails, sizeof fin, cudaMemcpyDeviceToHost));
+        n_wide = fin[0];
+        depth = fin[4];
+        if (fin[2] < fin[3]) depth = kMaxStack;  // levels left over: deeper than traversal supports
     } else {
-        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, wide, ctx->tris_leaf);
+        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tris_leaf);
         depth = 1;
     }
     cudaEventRecord(ev[6]);
     BUILD_TRY(cudaDeviceSynchronize());
-    BUILD_TRY(cudaMalloc(&ctx->nodes, sizeof(Node64) * (size_t)n_wide));
-    BUILD_TRY(cudaMemcpy(ctx->nodes, wide, sizeof(Node64) * (size_t)n_wide, cudaMemcpyDeviceToDevice));
-    cudaFree(wide);
+    if ((size_t)(nt - n_wide) * sizeof(Node64) > (64u << 20)) {  // give back a large unused tail
+        Node64* fit = nullptr;
+        BUILD_TRY(cudaMalloc(&fit, sizeof(Node64) * (size_t)n_wide));
+        BUILD_TRY(cudaMemcpy(fit, ctx->nodes, sizeof(Node64) * (size_t)n_wide, cudaMemcpyDeviceToDevice));
+        cudaFree(ctx->nodes);
+        ctx->nodes = fit;
+    }
     n_rec = n_wide;
     float ms[6];
     for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
@@ -531,6 +563,11 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     st.ms_emit = ms[5];
     st.ms_total = ms[0] + ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
     st.depth = depth;
+    {
+        unsigned int inversions = 0;
+        cudaMemcpy(&inversions, B.max_depth, sizeof inversions, cudaMemcpyDeviceToHost);
+        st.morton_sorted = inversions == 0 ? 1u : 0u;
+    }
     B.free_all();
     if (3 * depth + 1 > (unsigned)kMaxStack) { *too_deep = true; return PRT_OK; }  // <= 3 pushes per level
     ctx->n_nodes = n_rec;

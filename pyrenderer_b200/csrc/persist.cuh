@@ -21,6 +21,10 @@
 #include "bvh.cuh"
 #include "traverse.cuh"
 
+#ifndef PRT_VISITS_PER_ITER
+#define PRT_VISITS_PER_ITER 3  // record visits between two rounds of warp votes (profiles/r1_sweeps.txt)
+#endif
+
 namespace prt {
 
 // scheduling knobs live in SceneDev (refill_idle: refill when at least this many lanes are idle;
@@ -87,7 +91,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
         }
         // ---- one record visit for every lane that is at an internal record
 #pragma unroll
-        for (int rep = 0; rep < 2; ++rep)
+        for (int rep = 0; rep < PRT_VISITS_PER_ITER; ++rep)
         if (has_ray && !(cur & kLeafFlag)) {
             if (COUNT) ++c_nodes;
             NodeHits h;

@@ -75,13 +75,14 @@ struct ApiIO {
     const float4* rays;
     void* out;
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
-        ro = __ldg(rays + 2ull * k);
-        rd = __ldg(rays + 2ull * k + 1);
+        // rays and hits stream through once: evict-first, so they do not push the BVH out of L2
+        ro = __ldcs(rays + 2ull * k);
+        rd = __ldcs(rays + 2ull * k + 1);
         tag = k;
     }
     __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
         if (MODE == MODE_CLOSEST)
-            reinterpret_cast<float4*>(out)[tag] = make_float4(gid >= 0 ? t : 0.0f, u, v, __int_as_float(gid));
+            __stcs(reinterpret_cast<float4*>(out) + tag, make_float4(gid >= 0 ? t : 0.0f, u, v, __int_as_float(gid)));
         else
             reinterpret_cast<uint8_t*>(out)[tag] = gid >= 0 ? 1 : 0;
     }
