@@ -318,7 +318,7 @@ def main():
         for k in range(2):
             rctx.render_host(rctx.render_params(seed=1, spp_begin=k * spp, spp_end=(k + 1) * spp, max_depth=depth), host_acc)
         r_e2e_ms = (time.perf_counter() - t0) * 1e3 / 2
-        waves = (spp * W * H + (4 << 20) - 1) // (4 << 20)
+        waves = (spp * W * H + (16 << 20) - 1) // (16 << 20)
         launches_render = waves * (2 + 4 * depth)
         render = {"workload": f"cornell-box {W}x{H}, max depth {depth}, {spp} spp/step/GPU, sample-sharded"
                               + (", 1 NCCL all-reduce of the fp32 accum per step" if world > 1 else ""),

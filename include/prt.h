@@ -125,7 +125,7 @@ typedef struct {
 typedef struct {
     uint32_t max_leaf_tris; /* 1..7, default 4 */
     float cost_node;        /* SAH traversal cost, default 1.0 */
-    float cost_tri;         /* SAH intersection cost, default 1.0 */
+    float cost_tri;         /* SAH intersection cost, default 2.0 */
     uint32_t rotations;     /* 1 = SAH tree rotations during refit (default 1) */
 } prt_bvh_options;
 
@@ -189,7 +189,7 @@ int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev,
                int32_t* prim_ids_dev, void* stream);
 /* same with a HOST accumulation buffer (upload, render, download; synchronous) */
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
-/* paths per wavefront wave (default 4 Mi); 0 keeps the current value */
+/* paths per wavefront wave (default 16 Mi = 2.2 GB of path state); 0 keeps the current value */
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths);
 
 int prt_get_counters(prt_ctx* ctx, prt_counters* out); /* synchronous */

@@ -48,6 +48,30 @@ def main():
         ctx.set_triangles_dev(tris, 1_000_000)
         print(ctx.build_bvh(max_leaf_tris=1))
         print(measure(ctx, r, hits))
+    elif mode == "render_wave":
+        from pyrenderer_b200.io_utils.read_tungsten import read_file
+        from pyrenderer_b200.main import DEFAULT_SCENE
+        scene, cam = read_file(DEFAULT_SCENE)
+        a = scene.arrays()
+        for leaf in (1, 2, 4):
+            for wave in (1 << 20, 4 << 20, 16 << 20):
+                ctx = _abi.Context(0)
+                ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])
+                st = ctx.build_bvh(max_leaf_tris=leaf)
+                ctx.set_wave_paths(wave)
+                iview, sw, sh, focal, W, H = cam.device_record()
+                ctx.set_camera(iview, sw, sh, focal, W, H)
+                acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+                best = 1e9
+                for rep in range(3):
+                    ctx.reset_counters()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); ctx.render(ctx.render_params(seed=1, spp_begin=16 * rep, spp_end=16 * rep + 16, max_depth=8), acc); e1.record()
+                    torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                c = ctx.counters()
+                print(f"render leaf {leaf} nodes {st['n_nodes']} wave {wave >> 20}M: {best:7.2f} ms / 16 spp  {(c['rays_closest'] + c['rays_shadow']) / best / 1e3:8.1f} Mrays/s", flush=True)
+                ctx.close()
     elif mode in ("render", "render1"):
         from pyrenderer_b200.io_utils.read_tungsten import read_file
         from pyrenderer_b200.main import DEFAULT_SCENE

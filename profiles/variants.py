@@ -10,9 +10,9 @@ VDIR = os.path.join(ROOT, "pyrenderer_b200", "variants")
 # depth 8/12/16 no effect -- none of them is in the tree any more; add -D switches here to try new ones.
 VARIANTS = {
     "base": (),
-    "visits1": ("-DPRT_VISITS_PER_ITER=1",),
-    "visits3": ("-DPRT_VISITS_PER_ITER=3",),
-    "visits4": ("-DPRT_VISITS_PER_ITER=4",),
+    "mb9": ("-DPRT_MIN_BLOCKS=9",),
+    "mb10": ("-DPRT_MIN_BLOCKS=10",),
+    "mb12": ("-DPRT_MIN_BLOCKS=12",),
 }
 if sys.argv[1] == "build":
     from pyrenderer_b200 import build

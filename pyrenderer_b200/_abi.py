@@ -175,7 +175,7 @@ class Context:
         self._check(self.lib.prt_scene_set_triangles_dev(self.h, _dev_ptr(verts_dev), int(nt),
                                                          _stream_ptr(stream)))
 
-    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=1.0, rotations=1):
+    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=2.0, rotations=1):
         opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations))
         st = PrtBvhStats()
         self._check(self.lib.prt_bvh_build(self.h, C.byref(opts), C.byref(st)))

@@ -579,7 +579,9 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
 
 int build_bvh(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats) {
     prt_bvh_options o;
-    o.max_leaf_tris = 4; o.cost_node = 1.0f; o.cost_tri = 1.0f; o.rotations = 1;
+    // cost_tri 2: coplanar pairs (quads) still collapse into one leaf, random soups do not
+    // (profiles/r1_sweeps.txt: soup-1M prefers 1-triangle leaves, Cornell 2..4)
+    o.max_leaf_tris = 4; o.cost_node = 1.0f; o.cost_tri = 2.0f; o.rotations = 1;
     if (opts) o = *opts;
     if (o.max_leaf_tris < 1 || o.max_leaf_tris > 7) { ctx->set_error("bvh: max_leaf_tris must be in 1..7"); return PRT_ERR_INVALID; }
     if (!ctx->scene_set) { ctx->set_error("bvh: no scene"); return PRT_ERR_STATE; }

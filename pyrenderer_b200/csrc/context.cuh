@@ -49,7 +49,7 @@ struct prt_ctx {
 
     // wavefront state (wavefront.cu)
     void* wf = nullptr;
-    uint64_t wave_paths = 4ull << 20;
+    uint64_t wave_paths = 16ull << 20;
 
     void set_error(const char* fmt, ...) {
         va_list ap;

@@ -111,6 +111,60 @@ __device__ __forceinline__ int tri_watertight(const RayW& r, float3 p0, float3 p
     }
 }
 
+// ---- throughput variant --------------------------------------------------------------------
+// Same watertight construction, organised for SIMT: the axis permutation + shear is folded into
+// three per-ray coefficient vectors (x' = A.cx, y' = A.cy, z' = A.cz; two of the three
+// coefficients of cx, cy are 1 and 0, so the products are exact), which removes the 3-way branch
+// on the dominant axis that the select form compiles into, and t uses one IEEE reciprocal
+// instead of two divisions.  Every vertex still maps to the same sheared coordinates in both
+// triangles that share it, and the edge functions are still two rounded products and one
+// subtraction, so shared edges stay watertight.  No error bounds: EXACT mode uses the version above.
+struct RayWF {
+    float3 o, cx, cy, cz;
+};
+
+__device__ __forceinline__ RayWF make_raywf(float3 o, float3 d) {
+    const RayW r = make_rayw(o, d);
+    RayWF f;
+    f.o = o;
+    const float nsx = -r.Sx, nsy = -r.Sy;
+    if (r.kz == 0) {         // kx = 1, ky = 2
+        f.cx = make_float3(nsx, 1.f, 0.f); f.cy = make_float3(nsy, 0.f, 1.f); f.cz = make_float3(r.Sz, 0.f, 0.f);
+    } else if (r.kz == 1) {  // kx = 2, ky = 0
+        f.cx = make_float3(0.f, nsx, 1.f); f.cy = make_float3(1.f, nsy, 0.f); f.cz = make_float3(0.f, r.Sz, 0.f);
+    } else {                 // kx = 0, ky = 1
+        f.cx = make_float3(1.f, 0.f, nsx); f.cy = make_float3(0.f, 1.f, nsy); f.cz = make_float3(0.f, 0.f, r.Sz);
+    }
+    return f;
+}
+
+__device__ __forceinline__ float dot3f(float3 a, float3 c) { return fmaf(a.z, c.z, fmaf(a.y, c.y, a.x * c.x)); }
+
+__device__ __forceinline__ int tri_watertight_fast(const RayWF& r, float3 p0, float3 p1, float3 p2,
+                                                   float t_lo, float bound, TriHit& h) {
+    const float3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
+    const float Ax = dot3f(A, r.cx), Ay = dot3f(A, r.cy);
+    const float Bx = dot3f(B, r.cx), By = dot3f(B, r.cy);
+    const float Cx = dot3f(C, r.cx), Cy = dot3f(C, r.cy);
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)(__dmul_rn((double)Cx, (double)By) - __dmul_rn((double)Cy, (double)Bx));
+        V = (float)(__dmul_rn((double)Ax, (double)Cy) - __dmul_rn((double)Ay, (double)Cx));
+        W = (float)(__dmul_rn((double)Bx, (double)Ay) - __dmul_rn((double)By, (double)Ax));
+    }
+    if (fminf(U, fminf(V, W)) < 0.0f && fmaxf(U, fmaxf(V, W)) > 0.0f) return 0;
+    const float det = U + V + W;
+    if (det == 0.0f) return 0;
+    const float T = fmaf(U, dot3f(A, r.cz), fmaf(V, dot3f(B, r.cz), W * dot3f(C, r.cz)));
+    const float inv = __frcp_rn(det);
+    const float t = T * inv;
+    if (!(t >= t_lo && t <= bound)) return 0;
+    h.t = t; h.u = V * inv; h.v = W * inv; h.dt = 0.f;
+    return 1;
+}
+
 // ---- FP64 replay of the reference kernel -------------------------------------
 __device__ __forceinline__ double ddot3(const double* x, const double* y) {
     return __dadd_rn(__dadd_rn(__dmul_rn(x[0], y[0]), __dmul_rn(x[1], y[1])), __dmul_rn(x[2], y[2]));

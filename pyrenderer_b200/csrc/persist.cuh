@@ -25,6 +25,10 @@
 #define PRT_VISITS_PER_ITER 3  // record visits between two rounds of warp votes (profiles/r1_sweeps.txt)
 #endif
 
+#ifndef PRT_MIN_BLOCKS
+#define PRT_MIN_BLOCKS 1  // __launch_bounds__ min blocks/SM of the persistent traversal kernels
+#endif
+
 namespace prt {
 
 // scheduling knobs live in SceneDev (refill_idle: refill when at least this many lanes are idle;
@@ -41,7 +45,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
     uint2 ovf[kPStackOvf];
     bool has_ray = false, exhausted = false;
     // per-ray state
-    RayW rw;
+    RayWF rw;
     RayBox rb;
     float tmin = 0.f, tmax = 0.f, bt = 0.f, bu = 0.f, bv = 0.f;
     int bgid = -1, sp = 0;
@@ -72,7 +76,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     float4 ro, rd;
                     io.load(k, ro, rd, tag);
                     const float3 o = xyz(ro), d = xyz(rd);
-                    rw = make_rayw(o, d);
+                    rw = make_raywf(o, d);
                     rb = make_raybox(o, d);
                     tmin = ro.w; tmax = rd.w;
                     bt = tmax; bu = 0.f; bv = 0.f; bgid = -1;
@@ -115,8 +119,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                     if (COUNT) ++c_tris;
                     TriHit h;
-                    bool unc;
-                    if (tri_watertight<false>(rw, xyz(a), xyz(b), xyz(c), tmin, MODE == MODE_CLOSEST ? bt : tmax, 0.f, h, unc)) {
+                    if (tri_watertight_fast(rw, xyz(a), xyz(b), xyz(c), tmin, MODE == MODE_CLOSEST ? bt : tmax, h)) {
                         const int gid = __float_as_int(a.w);
                         if (MODE == MODE_CLOSEST) {
                             if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; }

@@ -89,7 +89,7 @@ struct ApiIO {
 };
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out,
                         unsigned int* fetch, Counters* ctr) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];

@@ -139,7 +139,7 @@ struct QueueClosestIO {
     }
 };
 
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
                const uint32_t* __restrict__ queue, unsigned int* cnt) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
@@ -167,7 +167,7 @@ struct QueueShadowIO {
     }
 };
 
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 shadow_kernel(SceneDev sc, const float4* __restrict__ srays, const float4* __restrict__ scontrib,
               float4* L, unsigned int* cnt) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];

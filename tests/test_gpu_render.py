@@ -104,7 +104,7 @@ def test_render_is_deterministic_and_partition_invariant(gpu_ctx, cornell):
     W, H = 96, 64
     setup_cornell(gpu_ctx, cornell, W, H)
     kw = dict(seed=5, max_depth=6)
-    gpu_ctx.set_wave_paths(4 << 20)
+    gpu_ctx.set_wave_paths(16 << 20)
     a1, _ = gpu_render(gpu_ctx, W, H, spp_begin=0, spp_end=16, **kw)
     a2, _ = gpu_render(gpu_ctx, W, H, spp_begin=0, spp_end=16, **kw)
     assert np.array_equal(a1, a2)
@@ -119,7 +119,7 @@ def test_render_is_deterministic_and_partition_invariant(gpu_ctx, cornell):
     assert np.allclose(a3, a1, rtol=2e-6, atol=1e-6)  # fp32 summation order differs
     gpu_ctx.set_wave_paths(W * H * 3)  # 3 samples per wave -> waves of 3,3,3,3,3,1
     a4, _ = gpu_render(gpu_ctx, W, H, spp_begin=0, spp_end=16, **kw)
-    gpu_ctx.set_wave_paths(4 << 20)
+    gpu_ctx.set_wave_paths(16 << 20)
     assert np.allclose(a4, a1, rtol=2e-6, atol=1e-6)
 
 
