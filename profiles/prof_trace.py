@@ -1,4 +1,4 @@
-"""Small driver for ncu: 1M-triangle soup, closest-hit batches of 2^22 incoherent rays.
+"""Small driver for ncu: 1M-triangle soup, closest-hit batches of 2^24 incoherent rays (= one bench.py step).
 usage: python profiles/prof_trace.py [n_launches]"""
 import os
 import sys
@@ -11,7 +11,7 @@ from bench import soup  # noqa: E402
 from pyrenderer_b200 import _abi  # noqa: E402
 
 n_launch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-N = 1 << 22
+N = 1 << 24  # the bench launch: 2^24 rays
 dev = torch.device("cuda", 0)
 ctx = _abi.Context(0)
 ctx.set_triangles_dev(torch.from_numpy(soup(1_000_000)).to(dev), 1_000_000)
