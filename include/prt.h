@@ -126,7 +126,7 @@ typedef struct {
     uint32_t max_leaf_tris; /* 1..7, default 4 */
     float cost_node;        /* SAH traversal cost, default 1.0 */
     float cost_tri;         /* SAH intersection cost, default 2.0 */
-    uint32_t rotations;     /* 1 = SAH tree rotations during refit (default 1) */
+    uint32_t rotations;     /* number of bottom-up SAH rotation passes during refit (0 = none, default 1) */
 } prt_bvh_options;
 
 int prt_abi_version(void);

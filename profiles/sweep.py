@@ -43,6 +43,13 @@ def main():
                     st = ctx.build_bvh(max_leaf_tris=leaf, cost_node=cn, cost_tri=ct, rotations=rot)
                     m, nn, nt = measure(ctx, r, hits)
                     print(f"leaf {leaf} cn {cn} ct {ct} rot {rot}: {m:8.1f} Mrays/s  N_node {nn:6.1f} N_tri {nt:5.1f} nodes {st['n_nodes']} depth {st['depth']} sah {st['sah_cost']:.1f} build {st['ms_total']:.2f} ms", flush=True)
+    elif mode == "rot":
+        ctx = _abi.Context(0)
+        for rot in (0, 1, 2, 3, 4, 6):
+            ctx.set_triangles_dev(tris, 1_000_000)
+            st = ctx.build_bvh(max_leaf_tris=1, rotations=rot)
+            m, nn, nt = measure(ctx, r, hits)
+            print(f"rotation passes {rot}: {m:8.1f} Mrays/s  N_node {nn:6.2f} N_tri {nt:5.2f} sah {st['sah_cost']:.1f} build {st['ms_total']:.2f} ms (refit {st['ms_refit']:.2f})", flush=True)
     elif mode == "util":
         ctx = _abi.Context(0)
         ctx.set_triangles_dev(tris, 1_000_000)

@@ -502,8 +502,13 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     RefitParams P;
     P.n = n; P.max_leaf = opt.max_leaf_tris; P.cn = opt.cost_node; P.ct = opt.cost_tri;
     P.rotations = (int)opt.rotations;
-    refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[sorted], B.left, B.right, B.parent, B.bmin, B.bmax,
-                            B.tcount, B.icount, B.collapsed, B.flags, P);
+    // rotations = k > 1 repeats the bottom-up pass: every pass re-derives boxes and costs from the
+    // leaves and applies the best rotation per node again (the topology from the last pass is kept)
+    for (int pass = 0; pass < (P.rotations > 1 ? P.rotations : 1); ++pass) {
+        if (pass) cudaMemsetAsync(B.flags, 0, sizeof(unsigned int) * (nt > 1 ? nt - 1 : 1));
+        refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[sorted], B.left, B.right, B.parent, B.bmin, B.bmax,
+                                B.tcount, B.icount, B.collapsed, B.flags, P);
+    }
     cudaEventRecord(ev[4]);
     BUILD_TRY(cudaGetLastError());
     uint32_t n_rec = 1;

@@ -64,18 +64,18 @@ __device__ __forceinline__ float2 concentric_sample_disk(float u1, float u2) {
 __device__ __forceinline__ float3 cosine_sample_hemisphere(float3 n_in, float u1, float u2) {
     float2 d = concentric_sample_disk(u1, u2);
     float z = sqrtf(fmaxf(0.0f, 1.0f - d.x * d.x - d.y * d.y));
-    float3 n = normalize(n_in);
+    float3 n = normalize(n_in);  // exact: the n.y == +-1 special case below must fire as in the reference
     float3 r1, r2;
     if (fabsf(n.y - 1.0f) < 1.17549435e-38f) {
         r1 = make_float3(1.f, 0.f, 0.f); r2 = make_float3(0.f, 0.f, 1.f); n = make_float3(0.f, 1.f, 0.f);
     } else if (fabsf(n.y + 1.0f) < 1.17549435e-38f) {
         r1 = make_float3(1.f, 0.f, 0.f); r2 = make_float3(0.f, 0.f, 1.f); n = make_float3(0.f, -1.f, 0.f);
     } else {
-        r1 = normalize(cross(n, make_float3(0.f, 1.f, 0.f)));
-        r2 = normalize(cross(r1, n));
+        r1 = normalize_fast(cross(n, make_float3(0.f, 1.f, 0.f)));
+        r2 = normalize_fast(cross(r1, n));
     }
     float3 w = r1 * d.x + r2 * d.y + n * z;
-    return normalize(w);
+    return normalize_fast(w);
 }
 
 // core/bsdf_taichi.py:6-22

@@ -246,7 +246,7 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                         nee = true;
                     } else {
                         float3 ns = (!front && !m.two_sided) ? -n : n;
-                        float3 ud = normalize(d);
+                        float3 ud = normalize_fast(d);
                         if (m.type == PRT_MAT_MIRROR) {
                             wi = reflect(ud, ns);
                         } else if (m.type == PRT_MAT_CONDUCTOR) {
@@ -261,7 +261,7 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                             else wi = refract(ud, ns, ratio);
                         }
                         if (ok) {
-                            wi = normalize(wi);
+                            wi = normalize_fast(wi);
                             b = b * alb;
                         }
                     }
@@ -278,8 +278,8 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                             float4 lsh = __ldg(sc.shade + lt);
                             float3 w = p2 - p;
                             float dist2 = dot(w, w);
-                            float dist = sqrtf(dist2);
-                            w = make_float3(w.x / dist, w.y / dist, w.z / dist);
+                            float idist = rsqrtf(dist2), dist = dist2 * idist;
+                            w = make_float3(w.x * idist, w.y * idist, w.z * idist);
                             float dot1 = dot(n, w), dot2 = -dot(xyz(lsh), w);
                             if (dot1 > 0.0f && dot2 > 0.0f) {
                                 const prt_material lm = sc.mats[__float_as_uint(lsh.w)];

@@ -195,6 +195,22 @@ def test_any_and_all_hits(gpu_ctx):
         assert np.array_equal(occ.cpu().numpy(), occ_o)
         assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o)  # the full hit SET per ray
         assert np.array_equal(sums.cpu().numpy().view(np.uint64), sums_o)
+    # throughput (plain FP32, persistent-warp) any-hit kernel: disagreement must be tiny
+    gpu_ctx.trace_any(r, rays.shape[0], occ, 0)
+    torch.cuda.synchronize()
+    frac = np.mean(occ.cpu().numpy() != occ_o)
+    print(f"[any-hit] FP32-only mismatch fraction {frac:.2e}")
+    assert frac < 1e-4
+    # counted twin of the throughput closest-hit kernel returns the same hits as the plain one
+    h0 = torch.empty((rays.shape[0], 4), dtype=torch.float32, device="cuda")
+    h1 = torch.empty((rays.shape[0], 4), dtype=torch.float32, device="cuda")
+    gpu_ctx.reset_counters()
+    gpu_ctx.trace_closest(r, rays.shape[0], h0, 0)
+    gpu_ctx.trace_closest(r, rays.shape[0], h1, COUNT)
+    torch.cuda.synchronize()
+    assert torch.equal(h0.view(torch.int32), h1.view(torch.int32))  # bit compare (tri == -1 is a NaN pattern)
+    c = gpu_ctx.counters()
+    assert c["rays_closest"] == rays.shape[0] and c["node_visits"] > rays.shape[0] and c["tri_tests"] > 0
 
 
 def test_edge_cases(gpu_ctx, cornell):
