@@ -187,6 +187,12 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n,
  * prim_ids_dev (optional) [h][w][spp_end-spp_begin] i32 primary-hit triangle ids. */
 int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev,
                int32_t* prim_ids_dev, void* stream);
+/* path tracing from caller-supplied rays: replaces `e, r = path_tracing(ray, a_scene)` under the
+ * reference's own ray generation (main.py:21-23,33-35).  For every ray i, samples
+ * [spp_begin, spp_end) are traced (Philox stream "pixel" = i) and ADDED to radiance_dev[i] =
+ * (r, g, b sums, sample count).  prim_ids_dev optional [n][spp_end-spp_begin]. */
+int prt_trace_paths(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, const prt_render_params* params,
+                    float* radiance_dev, int32_t* prim_ids_dev, void* stream);
 /* same with a HOST accumulation buffer (upload, render, download; synchronous) */
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
 /* paths per wavefront wave (default 16 Mi = 2.2 GB of path state); 0 keeps the current value */

@@ -58,7 +58,7 @@ class PrtCounters(C.Structure):
 EXPORTS = [
     "prt_abi_version", "prt_create", "prt_destroy", "prt_last_error", "prt_scene_set_triangles",
     "prt_scene_set_triangles_dev", "prt_bvh_build", "prt_camera_set", "prt_generate_rays",
-    "prt_trace_closest", "prt_trace_any", "prt_trace_all", "prt_trace_closest_host", "prt_render",
+    "prt_trace_closest", "prt_trace_any", "prt_trace_all", "prt_trace_closest_host", "prt_render", "prt_trace_paths",
     "prt_render_host", "prt_set_wave_paths", "prt_get_counters", "prt_reset_counters",
     "prt_synchronize",
 ]
@@ -97,6 +97,7 @@ def load():
     lib.prt_trace_closest_host.argtypes = [vp, vp, u64, vp, u32]
     lib.prt_render.argtypes = [vp, C.POINTER(PrtRenderParams), vp, vp, vp]
     lib.prt_render_host.argtypes = [vp, C.POINTER(PrtRenderParams), vp]
+    lib.prt_trace_paths.argtypes = [vp, vp, u64, C.POINTER(PrtRenderParams), vp, vp, vp]
     lib.prt_set_wave_paths.argtypes = [vp, u64]
     lib.prt_get_counters.argtypes = [vp, C.POINTER(PrtCounters)]
     lib.prt_reset_counters.argtypes = [vp]
@@ -241,6 +242,10 @@ class Context:
     def render(self, params, accum_dev, prim_ids_dev=None, stream=None):
         self._check(self.lib.prt_render(self.h, C.byref(params), _dev_ptr(accum_dev),
                                         _dev_ptr(prim_ids_dev), _stream_ptr(stream)))
+
+    def trace_paths(self, rays_dev, n, params, radiance_dev, prim_ids_dev=None, stream=None):
+        self._check(self.lib.prt_trace_paths(self.h, _dev_ptr(rays_dev), int(n), C.byref(params),
+                                             _dev_ptr(radiance_dev), _dev_ptr(prim_ids_dev), _stream_ptr(stream)))
 
     def render_host(self, params, accum):
         assert accum.dtype == np.float32 and accum.flags.c_contiguous

@@ -50,6 +50,31 @@ def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_O
     return (accum, ids) if want_prim_ids else accum
 
 
+def path_tracing(ray, a_scene, ray_logger=None, spp=1, max_depth=5, seed=1, sample_index=0, device=0):
+    """Drop-in for the reference's ``e, r = path_tracing(ray, a_scene[, ray_logger])`` (call
+    sites main.py:22,34,78; the function itself is missing at the reference's HEAD).
+    ``ray`` is one host-side Ray or a sequence of them.  Returns ``(e, r)`` with ``e + r`` the
+    mean radiance of ``spp`` paths started on the ray: ``e`` = what a directly visible emitter
+    contributes, ``r`` = everything gathered after the first bounce."""
+    torch = _torch()
+    rays = ray if isinstance(ray, (list, tuple)) else [ray]
+    rec = np.array([[*r.position, T_MIN, *r.direction, T_MAX] for r in rays], np.float32)
+    ctx = a_scene.commit(device)
+    d = torch.from_numpy(rec).to(f"cuda:{device}")
+    rad = torch.zeros((len(rays), 4), dtype=torch.float32, device=d.device)
+    ids = torch.empty((len(rays), spp), dtype=torch.int32, device=d.device)
+    params = ctx.render_params(seed=seed, spp_begin=sample_index, spp_end=sample_index + spp,
+                               max_depth=max_depth, tmin=T_MIN, tmax=T_MAX)
+    ctx.trace_paths(d, len(rays), params, rad, ids)
+    out = rad.cpu().numpy().astype(np.float64)
+    mean = out[:, :3] / np.maximum(out[:, 3:4], 1.0)
+    lights = set(int(t) for t in a_scene.arrays()["light_tris"])
+    direct = np.array([[int(t) in lights for t in row] for row in ids.cpu().numpy()]).all(axis=1)
+    e = np.where(direct[:, None], mean, 0.0)
+    r = np.where(direct[:, None], 0.0, mean)
+    return (e[0], r[0]) if not isinstance(ray, (list, tuple)) else (e, r)
+
+
 def shard_samples(spp, rank, world):
     """Contiguous sample range of ``rank``: [r*S/G, (r+1)*S/G)."""
     return (spp * rank) // world, (spp * (rank + 1)) // world

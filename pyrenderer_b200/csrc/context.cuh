@@ -84,6 +84,6 @@ int build_bvh(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats);
 int generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int jitter, float tmin,
                   float tmax, float4* rays, cudaStream_t stream);
 int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim_ids,
-           cudaStream_t stream);
+           cudaStream_t stream, const float4* user_rays = nullptr, uint64_t n_user = 0);
 void wavefront_free(prt_ctx* ctx);
 }  // namespace prt

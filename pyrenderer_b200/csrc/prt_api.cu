@@ -299,6 +299,15 @@ int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev, 
     return render(ctx, params, accum_dev, prim_ids_dev, (cudaStream_t)stream);
 }
 
+int prt_trace_paths(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, const prt_render_params* params,
+                    float* radiance_dev, int32_t* prim_ids_dev, void* stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (n == 0) return PRT_OK;
+    if (!params || !rays_dev || !radiance_dev) { ctx->set_error("trace_paths: NULL argument"); return PRT_ERR_INVALID; }
+    return render(ctx, params, radiance_dev, prim_ids_dev, (cudaStream_t)stream, (const float4*)rays_dev, n);
+}
+
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host) {
     CHECK_CTX(ctx);
     USE_DEVICE(ctx);

@@ -124,6 +124,21 @@ __global__ void raygen_kernel(CamDev cam, WaveParams P, float4* rays, float4* be
     queue[pid] = pid;
 }
 
+// path start from caller-supplied rays (prt_trace_paths): "pixel" == ray index
+__global__ void init_paths_kernel(const float4* __restrict__ user_rays, WaveParams P, float4* rays, float4* beta,
+                                  float4* L, uint32_t* queue, unsigned int* cnt) {
+    uint32_t n_paths = P.npix * P.ns_wave;
+    uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid == 0) { cnt[0] = n_paths; cnt[1] = 0; cnt[2] = 0; cnt[3] = 0; cnt[4] = 0; }
+    if (pid >= n_paths) return;
+    uint32_t pixel = pid % P.npix;
+    rays[2 * (size_t)pid] = user_rays[2 * (size_t)pixel];
+    rays[2 * (size_t)pid + 1] = user_rays[2 * (size_t)pixel + 1];
+    beta[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+    L[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    queue[pid] = pid;
+}
+
 // persistent closest-hit over the current queue (persist.cuh: lane-level dynamic fetch)
 struct QueueClosestIO {
     const float4* rays;
@@ -403,14 +418,15 @@ static int wave_alloc(prt_ctx* ctx, uint64_t cap) {
     return PRT_OK;
 }
 
+// user_rays == nullptr: camera rays for every pixel (prt_render); else one path set per supplied ray
 int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim_ids,
-           cudaStream_t stream) {
+           cudaStream_t stream, const float4* user_rays, uint64_t n_user) {
     if (!ctx->scene_set || !ctx->bvh_built) { ctx->set_error("render: scene/BVH not ready"); return PRT_ERR_STATE; }
-    if (!ctx->cam_set) { ctx->set_error("render: camera not set"); return PRT_ERR_STATE; }
+    if (!user_rays && !ctx->cam_set) { ctx->set_error("render: camera not set"); return PRT_ERR_STATE; }
     if (p->spp_end < p->spp_begin) { ctx->set_error("render: spp_end < spp_begin"); return PRT_ERR_INVALID; }
     if (p->max_depth == 0 || p->spp_end == p->spp_begin) return PRT_OK;
-    const uint64_t npix = (uint64_t)ctx->cam.width * ctx->cam.height;
-    if (npix == 0 || npix > (1ull << 30)) { ctx->set_error("render: bad resolution"); return PRT_ERR_INVALID; }
+    const uint64_t npix = user_rays ? n_user : (uint64_t)ctx->cam.width * ctx->cam.height;
+    if (npix == 0 || npix > (1ull << 30)) { ctx->set_error("render: bad resolution / ray count"); return PRT_ERR_INVALID; }
     uint64_t per_wave = ctx->wave_paths / npix;
     if (per_wave == 0) per_wave = 1;
     const uint32_t ns_total = p->spp_end - p->spp_begin;
@@ -419,7 +435,7 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
     if (rc != PRT_OK) return rc;
     WaveState* w = (WaveState*)ctx->wf;
     SceneDev sc = ctx->scene_dev();
-    CamDev cam = cam_dev(ctx->cam);
+    CamDev cam = cam_dev(ctx->cam);  // unused with user rays
     WaveParams P;
     P.seed = p->seed; P.npix = (uint32_t)npix; P.spp_begin = p->spp_begin; P.ns_total = ns_total;
     P.rr_start = p->rr_start;
@@ -429,7 +445,10 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
         P.s_begin = s;
         P.ns_wave = (uint32_t)((p->spp_end - s) < per_wave ? (p->spp_end - s) : per_wave);
         uint32_t n_paths = P.npix * P.ns_wave;
-        raygen_kernel<<<(n_paths + 255) / 256, 256, 0, stream>>>(cam, P, w->rays, w->beta, w->L, w->queue[0], w->cnt);
+        if (user_rays)
+            init_paths_kernel<<<(n_paths + 255) / 256, 256, 0, stream>>>(user_rays, P, w->rays, w->beta, w->L, w->queue[0], w->cnt);
+        else
+            raygen_kernel<<<(n_paths + 255) / 256, 256, 0, stream>>>(cam, P, w->rays, w->beta, w->L, w->queue[0], w->cnt);
         for (uint32_t b = 0; b < p->max_depth; ++b) {
             uint32_t* qin = w->queue[b & 1];
             uint32_t* qout = w->queue[(b & 1) ^ 1];

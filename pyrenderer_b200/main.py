@@ -55,6 +55,31 @@ def main(scene_file=DEFAULT_SCENE, samples=8, max_depth=5, width=None, height=No
     return image
 
 
+def main_progressive(scene_file=DEFAULT_SCENE, iterations=1001, max_depth=16, seed=1, out="out.png",
+                     interval=10, save_every=100, device=0):
+    """Progressive driver in the shape of the reference's Taichi loop (main_taichi.py:102-127):
+    one sample per pixel per iteration into the same accumulation buffer, a "samples/s" line
+    every `interval` iterations, sqrt-tonemapped image every `save_every`, stop after `iterations`.
+    Exactly resumable: iteration k is Philox sample index k."""
+    import torch
+    a_scene, a_camera = read_file(scene_file)
+    accum = tracing.new_accum(a_camera, device)
+    last_t = time.time()
+    for iteration in range(iterations):
+        tracing.render(a_scene, a_camera, spp=1, max_depth=max_depth, seed=seed, spp_begin=iteration,
+                       accum=accum, device=device)
+        if iteration % interval == 0:
+            torch.cuda.synchronize()
+            print("{:.2f} samples/s ({} iterations)".format(interval / max(time.time() - last_t, 1e-9), iteration))
+            last_t = time.time()
+        if iteration % save_every == 0 and iteration > 0 and out:
+            write_png(out, tracing.to_uint8(tracing.to_image(accum, "sqrt")))
+    torch.cuda.synchronize()
+    if out:
+        write_png(out, tracing.to_uint8(tracing.to_image(accum, "sqrt")))
+    return accum
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--scene", default=DEFAULT_SCENE)
@@ -65,5 +90,10 @@ if __name__ == "__main__":
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default="test.png")
     ap.add_argument("--tonemap", default=None, choices=[None, "sqrt", "reinhard"])
+    ap.add_argument("--progressive", type=int, default=0, metavar="N",
+                    help="main_taichi.py-style loop: N iterations of 1 spp into one buffer")
     a = ap.parse_args()
+    if a.progressive:
+        main_progressive(a.scene, a.progressive, a.max_depth, a.seed, a.out)
+        raise SystemExit(0)
     main(a.scene, a.samples, a.max_depth, a.width, a.height, a.seed, a.out, a.tonemap)

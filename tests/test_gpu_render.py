@@ -234,3 +234,37 @@ def test_python_entry_points(cornell):
     assert np.allclose(res["normal"], [0, 0, 1], atol=1e-6) and res["bsdf"].emitting_light == 0
     miss = scene.hit(Ray(np.array([0.0, 1.0, 6.8]), np.array([0.0, 0.0, 1.0])))
     assert miss["hit"] is False
+
+
+def test_trace_paths_equals_render_on_generated_rays(gpu_ctx, cornell):
+    """prt_trace_paths on the camera's own rays (prt_generate_rays, pixel order) reproduces
+    prt_render sample for sample, bit for bit: same Philox streams, same kernels."""
+    torch = _torch()
+    W, H = 80, 48
+    setup_cornell(gpu_ctx, cornell, W, H)
+    kw = dict(seed=21, spp_begin=3, spp_end=4, max_depth=6)
+    a_render, ids_render = gpu_render(gpu_ctx, W, H, want_ids=True, **kw)
+    rays = torch.empty((H * W, 8), dtype=torch.float32, device="cuda")
+    gpu_ctx.generate_rays(rays, seed=21, s0=3, s1=4, jitter=True)
+    rad = torch.zeros((H * W, 4), dtype=torch.float32, device="cuda")
+    ids = torch.empty((H * W, 1), dtype=torch.int32, device="cuda")
+    gpu_ctx.trace_paths(rays, H * W, gpu_ctx.render_params(**kw), rad, ids)
+    torch.cuda.synchronize()
+    assert np.array_equal(rad.cpu().numpy().reshape(H, W, 4).astype(np.float64), a_render)
+    assert np.array_equal(ids.cpu().numpy().reshape(H, W, 1), ids_render)
+
+
+def test_path_tracing_drop_in(cornell):
+    """`e, r = path_tracing(ray, a_scene)` (reference call sites main.py:22,34,78)."""
+    from pyrenderer_b200.core import tracing
+    from pyrenderer_b200.core.ray import Ray
+    scene, cam = cornell
+    eye = np.array([0.0, 1.0, 6.8])
+    to_light = np.array([-0.005, 1.98, -0.03]) - eye
+    e, r = tracing.path_tracing(Ray(eye, to_light / np.linalg.norm(to_light)), scene, spp=4)
+    assert np.allclose(e, [0.9, 0.85, 0.7], atol=1e-6) and np.all(r == 0)
+    to_floor = np.array([0.5, 0.0, 0.5]) - eye
+    e, r = tracing.path_tracing(Ray(eye, to_floor / np.linalg.norm(to_floor)), scene, spp=64, max_depth=5)
+    assert np.all(e == 0) and np.all(r > 0) and np.isfinite(r).all()
+    es, rs = tracing.path_tracing([cam.generate_ray(np.array([u, 0.5])) for u in (0.1, 0.5, 0.9)], scene, spp=16)
+    assert es.shape == (3, 3) and rs.shape == (3, 3) and np.all(es + rs > 0)

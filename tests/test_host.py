@@ -210,3 +210,36 @@ def test_output_stage(tmp_path):
         assert np.array_equal(back, u8)
     except ImportError:
         pass
+
+
+def test_tungsten_mesh_primitive(tmp_path):
+    """a Tungsten scene that references an OBJ mesh loads into the same
+    Scene protocol (global triangle ids = file face order, transform applied, material bound)."""
+    import json
+    import shutil
+    from pyrenderer_b200.io_utils.read_tungsten import read_file
+    shutil.copy(CUBE_OBJ, tmp_path / "cube.obj")
+    scene_json = {
+        "bsdfs": [{"name": "m", "albedo": [0.2, 0.4, 0.6], "type": "lambert"},
+                  {"name": "glass", "type": "dielectric", "ior": 1.33},
+                  {"name": "L", "albedo": 1, "type": "null"}],
+        "primitives": [
+            {"type": "mesh", "file": "cube.obj", "bsdf": "m", "transform": {"position": [1, 2, 3], "scale": [2, 2, 2]}},
+            {"type": "cube", "bsdf": "glass", "transform": {}},
+            {"type": "quad", "bsdf": "L", "transform": {"position": [0, 5, 0]}}],
+        "camera": {"resolution": [32, 16], "fov": 40,
+                   "transform": {"position": [0, 0, 5], "look_at": [0, 0, 0], "up": [0, 1, 0]}}}
+    p = tmp_path / "scene.json"
+    p.write_text(json.dumps(scene_json))
+    scene, cam = read_file(str(p))
+    a = scene.arrays()
+    assert a["tris"].shape == (12 + 12 + 2, 3, 3)
+    assert np.allclose(a["tris"][:12].reshape(-1, 3).min(0), [1, 2, 3]) and np.allclose(a["tris"][:12].reshape(-1, 3).max(0), [3, 4, 5])
+    assert list(a["light_tris"]) == [24, 25]
+    m = a["materials"]
+    assert m[1]["type"] == 3 and abs(m[1]["ior"] - 1.33) < 1e-6 and m[1]["two_sided"] == 0
+    assert m[2]["type"] == 1 and m[0]["two_sided"] == 1
+    # outward normals of the OBJ cube (+normalize(e1 x e2)): they point away from the centre
+    c = a["tris"][:12].mean(axis=1) - np.array([2, 3, 4])
+    assert np.all(np.einsum("ij,ij->i", a["normals"][:12], c) > 0)
+    assert cam.aspect_ratio == 2.0
