@@ -1,7 +1,7 @@
 // bvh.cuh -- the quantised 4-wide node, its slab test and the per-lane stack.
 //
 // Node64 (common.cuh) holds the boxes of up to FOUR children, quantised to 8 bits per
-// plane in the node's own frame: plane = o + q * 2^(e-127).  The builder (bvh_build.cu)
+// plane in the node's own frame: plane = o + q * scale, scale a power of two per axis.  The builder (bvh_build.cu)
 // rounds lo down / hi up against this exact decode expression, so a decoded box always
 // contains the child's true FP32 box.  The slab test never decodes a box: per axis it
 // forms a = scale/d and b = (o - ray.o)/d once and each of the 24 planes costs one
@@ -48,42 +48,82 @@ __device__ __forceinline__ float qf(uint32_t w, int byte) {
     return (float)((w >> (8 * byte)) & 0xffu);  // I2F.U8 with a static byte selector
 }
 
+// Node fetch.  The traversal is bound by L1TEX wavefronts (one tag look-up per distinct
+// 128-byte line per load instruction, profiles/r1_trace_persistent_bvh4_ncu.txt: L1/TEX
+// throughput 89 %), so the 64-byte node is read with TWO 256-bit loads (sm_100
+// LDG.E.256, PTX ld.global.v8.b32) instead of four 128-bit ones.
+#ifndef PRT_LDG256
+#define PRT_LDG256 1
+#endif
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg_node(const Node64* __restrict__ node, uint4& w0, uint4& w1, uint4& w2, uint4& w3) {
+#if PRT_LDG256
+    ldg256(node, w0, w1);
+    ldg256(reinterpret_cast<const char*>(node) + 32, w2, w3);
+#else
+    const uint4* np = reinterpret_cast<const uint4*>(node);
+    w0 = __ldg(np); w1 = __ldg(np + 1); w2 = __ldg(np + 2); w3 = __ldg(np + 3);
+#endif
+}
+
 struct NodeHits {
-    float t[4];       // entry distance per child (valid where the mask bit is set)
+    float t[4];       // entry distance per child, +inf where the child is missed or absent
     uint32_t ref[4];
 };
 
-// Slab test of the four children.  Returns the hit mask.  EXACT widens every interval by
-// the forward error bound of t = q*a + b so that no box the exact ray touches is missed.
+// byte c of a plane word -> float.  PRT_QCONV_AXES of the three axes use the "folded" form:
+// PRMT builds the float 1 + q * 2^-15 (0x3F80qq00) on the ALU pipe and the slab becomes
+// t = f * (a * 2^15) + (b - a * 2^15); the other axes use I2F.U8 (XU pipe, 1/4 rate).  Splitting
+// the 24 conversions of a visit between the two pipes keeps either from limiting issue.
+#ifndef PRT_QCONV_AXES
+#define PRT_QCONV_AXES 2  // profiles/r1_sweeps.txt: 0 -> 1666, 1 -> 1706, 2 -> 1724, 3 -> 1689 Mrays/s (soup-1M)
+#endif
+template <bool FOLD>
+struct PlaneEval {
+    float a, b;
+    __device__ __forceinline__ PlaneEval(float scale, float origin, float ro, float idir) {
+        const float a0 = scale * idir, b0 = (origin - ro) * idir;
+        if (FOLD) { a = a0 * 32768.0f; b = b0 - a; } else { a = a0; b = b0; }
+    }
+    __device__ __forceinline__ float operator()(uint32_t w, int c) const {
+        if (FOLD) return fmaf(__uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t)(c << 4))), a, b);
+        return fmaf(qf(w, c), a, b);
+    }
+};
+
+// Slab test of the four children: h.t[c] = entry distance, +inf for a miss.  EXACT widens every
+// interval by the forward error bound of t = q*a + b so that no box the exact ray touches is missed.
 template <bool EXACT>
-__device__ __forceinline__ int node_test4(const Node64* __restrict__ node, const RayBox& r,
-                                          float tmin, float tmax, NodeHits& h) {
-    const uint4* np = reinterpret_cast<const uint4*>(node);
-    const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), w2 = __ldg(np + 2), w3 = __ldg(np + 3);
-    const float sx = __uint_as_float((w0.w & 0xffu) << 23);
-    const float sy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23);
-    const float sz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23);
-    const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
-    const float bx = (__uint_as_float(w0.x) - r.o.x) * r.idir.x, by = (__uint_as_float(w0.y) - r.o.y) * r.idir.y,
-                bz = (__uint_as_float(w0.z) - r.o.z) * r.idir.z;
-    const uint32_t nx = r.negx ? w1.y : w1.x, fx = r.negx ? w1.x : w1.y;
-    const uint32_t ny = r.negy ? w1.w : w1.z, fy = r.negy ? w1.z : w1.w;
-    const uint32_t nz = r.negz ? w2.y : w2.x, fz = r.negz ? w2.x : w2.y;
-    h.ref[0] = w2.z; h.ref[1] = w2.w; h.ref[2] = w3.x; h.ref[3] = w3.y;
+__device__ __forceinline__ void node_test4(const Node64* __restrict__ node, const RayBox& r,
+                                           float tmin, float tmax, NodeHits& h) {
+    uint4 w0, w1, w2, w3;
+    ldg_node(node, w0, w1, w2, w3);
+    constexpr int kFold = EXACT ? 0 : PRT_QCONV_AXES;
+    const PlaneEval<(kFold > 2)> px(__uint_as_float(w0.w), __uint_as_float(w0.x), r.o.x, r.idir.x);
+    const PlaneEval<(kFold > 1)> py(__uint_as_float(w1.x), __uint_as_float(w0.y), r.o.y, r.idir.y);
+    const PlaneEval<(kFold > 0)> pz(__uint_as_float(w1.y), __uint_as_float(w0.z), r.o.z, r.idir.z);
+    const uint32_t nx = r.negx ? w1.w : w1.z, fx = r.negx ? w1.z : w1.w;
+    const uint32_t ny = r.negy ? w2.y : w2.x, fy = r.negy ? w2.x : w2.y;
+    const uint32_t nz = r.negz ? w2.w : w2.z, fz = r.negz ? w2.z : w2.w;
+    h.ref[0] = w3.x; h.ref[1] = w3.y; h.ref[2] = w3.z; h.ref[3] = w3.w;
     float m = 0.0f;
     if (EXACT)
-        m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(bx) + 255.0f * fabsf(ax), fabsf(by) + 255.0f * fabsf(ay)),
-                                  fabsf(bz) + 255.0f * fabsf(az)));
-    int mask = 0;
+        m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(px.b) + 255.0f * fabsf(px.a), fabsf(py.b) + 255.0f * fabsf(py.a)),
+                                  fabsf(pz.b) + 255.0f * fabsf(pz.a)));
+    const float inf = __int_as_float(0x7f800000);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        float tn = fmaxf(fmaxf(fmaf(qf(nx, c), ax, bx), fmaf(qf(ny, c), ay, by)), fmaxf(fmaf(qf(nz, c), az, bz), tmin));
-        float tf = fminf(fminf(fmaf(qf(fx, c), ax, bx), fmaf(qf(fy, c), ay, by)), fminf(fmaf(qf(fz, c), az, bz), tmax));
+        float tn = fmaxf(fmaxf(px(nx, c), py(ny, c)), fmaxf(pz(nz, c), tmin));
+        float tf = fminf(fminf(px(fx, c), py(fy, c)), fminf(pz(fz, c), tmax));
         if (EXACT) { tn -= m; tf += m; }
-        h.t[c] = tn;
-        if (tn <= tf && h.ref[c] != kNoChild) mask |= 1 << c;
+        // absent children carry inverted planes AND kNoChild: the planes alone are not proof
+        // (255*a + b can round to b for a tiny record far away)
+        h.t[c] = (tn <= tf && (c < 2 || h.ref[c] != kNoChild)) ? tn : inf;
     }
-    return mask;
 }
 
 // ---- per-lane stack of (child reference, entry distance) pairs -----------------------
@@ -130,21 +170,61 @@ __device__ __forceinline__ void cswap(float& ta, uint32_t& ra, float& tb, uint32
 // are pushed far-first (so the nearer ones pop first); no hit -> pop.  Written without
 // data-dependent branches around the sorting network: in a warp the lanes have 0..4 hits
 // each, and serialising three code paths costs more than sorting unconditionally.
-__device__ __forceinline__ uint32_t descend(int mask, NodeHits& h, uint32_t saddr, uint2* ovf, int& sp,
-                                            float bound) {
-    const float inf = __int_as_float(0x7f800000);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) h.t[c] = (mask & (1 << c)) ? h.t[c] : inf;
-    cswap(h.t[0], h.ref[0], h.t[1], h.ref[1]);  // sorting network for 4; misses sort to the back
+__device__ __forceinline__ void sort_hits(NodeHits& h) {
+    cswap(h.t[0], h.ref[0], h.t[1], h.ref[1]);  // sorting network for 4; misses (+inf) sort to the back
     cswap(h.t[2], h.ref[2], h.t[3], h.ref[3]);
     cswap(h.t[0], h.ref[0], h.t[2], h.ref[2]);
     cswap(h.t[1], h.ref[1], h.t[3], h.ref[3]);
+#if !defined(PRT_SORT4)
     cswap(h.t[1], h.ref[1], h.t[2], h.ref[2]);
+#endif
+}
+
+#ifndef PRT_PUSH_UNCOND
+#define PRT_PUSH_UNCOND 1
+#endif
+// push the (sorted) hits 3, 2, 1.  Common case (three free shared-memory levels): three
+// unconditional stores, the stack pointer advances only past the valid ones -- no branch per child.
+__device__ __forceinline__ void push_far(const NodeHits& h, uint32_t saddr, uint2* ovf, int& sp) {
+    const float inf = __int_as_float(0x7f800000);
+#if PRT_PUSH_UNCOND
+    if (sp <= kPStack - 3) {
+#pragma unroll
+        for (int c = 3; c >= 1; --c) {
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)), "r"(h.ref[c]), "r"(__float_as_uint(h.t[c])) : "memory");
+            sp += h.t[c] < inf ? 1 : 0;
+        }
+        return;
+    }
+#endif
     if (h.t[3] < inf) sstack_push(saddr, ovf, sp, h.ref[3], h.t[3]);
     if (h.t[2] < inf) sstack_push(saddr, ovf, sp, h.ref[2], h.t[2]);
     if (h.t[1] < inf) sstack_push(saddr, ovf, sp, h.ref[1], h.t[1]);
-    if (mask == 0) return sstack_pop_live(saddr, ovf, sp, bound);
+}
+
+__device__ __forceinline__ uint32_t descend(NodeHits& h, uint32_t saddr, uint2* ovf, int& sp, float bound) {
+    const float inf = __int_as_float(0x7f800000);
+    sort_hits(h);
+    push_far(h, saddr, ovf, sp);
+    if (!(h.t[0] < inf)) return sstack_pop_live(saddr, ovf, sp, bound);
     return h.ref[0];
+}
+
+// Loop-free variant for the persistent traversal: a miss returns kRetry and the caller pops ONE
+// entry at its next visit slot (pop_once); a culled entry costs the lane that slot instead of
+// making the whole warp wait in a 3-lane pop loop.
+constexpr uint32_t kRetry = 0xFFFFFFFEu;  // has kLeafFlag set; not a valid leaf reference
+__device__ __forceinline__ uint32_t descend_lazy(NodeHits& h, uint32_t saddr, uint2* ovf, int& sp) {
+    const float inf = __int_as_float(0x7f800000);
+    sort_hits(h);
+    push_far(h, saddr, ovf, sp);
+    return h.t[0] < inf ? h.ref[0] : kRetry;
+}
+__device__ __forceinline__ uint32_t pop_once(uint32_t saddr, const uint2* ovf, int& sp, float bound) {
+    if (sp <= 0) return kDone;
+    float t;
+    const uint32_t ref = sstack_pop(saddr, ovf, sp, t);
+    return t <= bound ? ref : kRetry;
 }
 
 }  // namespace prt

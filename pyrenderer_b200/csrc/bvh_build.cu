@@ -343,10 +343,10 @@ __device__ __forceinline__ void write_record(Node64* out, const float o[3], cons
         }
     }
     uint4* p = reinterpret_cast<uint4*>(out);
-    p[0] = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), e[0] | (e[1] << 8) | (e[2] << 16));
-    p[1] = make_uint4(qlo[0], qhi[0], qlo[1], qhi[1]);
-    p[2] = make_uint4(qlo[2], qhi[2], ref[0], ref[1]);
-    p[3] = make_uint4(ref[2], ref[3], 0u, 0u);
+    p[0] = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), e[0] << 23);
+    p[1] = make_uint4(e[1] << 23, e[2] << 23, qlo[0], qhi[0]);
+    p[2] = make_uint4(qlo[1], qhi[1], qlo[2], qhi[2]);
+    p[3] = make_uint4(ref[0], ref[1], ref[2], ref[3]);
 }
 
 // level[0] = begin, level[1] = end of the current level in the queue, level[2] = depth so far

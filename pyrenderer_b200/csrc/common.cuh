@@ -21,10 +21,9 @@ constexpr uint32_t kNoChild = 0xFFFFFFFFu;   // absent child slot; also the "tra
 // the same bytes-per-child as a 32-byte 2-wide node (see DESIGN.md 2 for why 4-wide).
 struct Node64 {
     float ox, oy, oz;   // frame origin (node box min)
-    uint32_t em;        // ex | ey<<8 | ez<<16 : plane = o + q * 2^(e-127)
-    uint32_t qx_lo, qx_hi, qy_lo, qy_hi;  // byte c = child c : quantised lo / hi planes per axis
-    uint32_t qz_lo, qz_hi, ref0, ref1;    // child refs: record index, or kLeafFlag | first_tri<<3 | count,
-    uint32_t ref2, ref3, pad0, pad1;      // or kNoChild
+    float sx, sy, sz;   // plane = o + q * s, s = 2^k per axis (stored as the float itself: no decode)
+    uint32_t qx_lo, qx_hi, qy_lo, qy_hi, qz_lo, qz_hi;  // byte c = child c : quantised lo / hi planes per axis
+    uint32_t ref[4];    // child refs: record index, or kLeafFlag | first_tri<<3 | count, or kNoChild
 };
 static_assert(sizeof(Node64) == 64, "node must be 64 bytes");
 

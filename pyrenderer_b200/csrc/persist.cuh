@@ -25,8 +25,12 @@
 #define PRT_VISITS_PER_ITER 3  // record visits between two rounds of warp votes (profiles/r1_sweeps.txt)
 #endif
 
+#ifndef PRT_POP_LAZY
+#define PRT_POP_LAZY 0  // 1: one predicated pop per visit slot instead of the pop loop (measured: -1 % soup, -12 % Cornell)
+#endif
+
 #ifndef PRT_MIN_BLOCKS
-#define PRT_MIN_BLOCKS 1  // __launch_bounds__ min blocks/SM of the persistent traversal kernels
+#define PRT_MIN_BLOCKS 8  // __launch_bounds__ min blocks/SM of the persistent traversal kernels: caps ptxas at 64 registers
 #endif
 
 namespace prt {
@@ -95,20 +99,28 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
         }
         // ---- one record visit for every lane that is at an internal record
 #pragma unroll
-        for (int rep = 0; rep < PRT_VISITS_PER_ITER; ++rep)
-        if (has_ray && !(cur & kLeafFlag)) {
-            if (COUNT) ++c_nodes;
-            NodeHits h;
+        for (int rep = 0; rep < PRT_VISITS_PER_ITER; ++rep) {
             const float bound = MODE == MODE_CLOSEST ? bt : tmax;
-            const int m = node_test4<false>(sc.nodes + cur, rb, tmin, bound, h);
-            cur = descend(m, h, saddr, ovf, sp, bound);
+#if PRT_POP_LAZY
+            if (has_ray && cur == kRetry) cur = pop_once(saddr, ovf, sp, bound);
+#endif
+            if (has_ray && !(cur & kLeafFlag)) {
+                if (COUNT) ++c_nodes;
+                NodeHits h;
+                node_test4<false>(sc.nodes + cur, rb, tmin, bound, h);
+#if PRT_POP_LAZY
+                cur = descend_lazy(h, saddr, ovf, sp);
+#else
+                cur = descend(h, saddr, ovf, sp, bound);
+#endif
+            }
         }
 
         // ---- leaves: parked lanes go together
-        const bool at_leaf = has_ray && (cur & kLeafFlag) && cur != kDone;
+        const bool at_leaf = has_ray && (cur & kLeafFlag) && cur < kRetry;
         const unsigned leafm = __ballot_sync(FULL, at_leaf);
         // idle lanes keep cur == kDone, so "no leaf flag" == "still walking records"
-        const unsigned nodem = ~__ballot_sync(FULL, (cur & kLeafFlag) != 0u);
+        const unsigned nodem = __ballot_sync(FULL, (cur & kLeafFlag) == 0u || cur == kRetry);  // kRetry: walking again after its pop
         if (leafm && (__popc(leafm) >= sc.leaf_batch || nodem == 0)) {
             if (COUNT) { ++c_lphases; c_llanes += __popc(leafm); }
             if (at_leaf) {
@@ -129,7 +141,11 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                         }
                     }
                 }
+#if PRT_POP_LAZY
+                cur = stop ? kDone : kRetry;
+#else
                 cur = stop ? kDone : sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? bt : tmax);
+#endif
             }
         }
         if (has_ray && cur == kDone) {

@@ -77,8 +77,8 @@ __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 
         if (!(cur & kLeafFlag)) {
             if (COUNT) ++res.n_nodes;
             NodeHits h;
-            const int m = node_test4<EXACT>(sc.nodes + cur, rb, tmin, bound, h);
-            cur = descend(m, h, saddr, ovf, sp, bound);
+            node_test4<EXACT>(sc.nodes + cur, rb, tmin, bound, h);
+            cur = descend(h, saddr, ovf, sp, bound);
         } else {
             uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
             if (process_tris<MODE, EXACT, COUNT>(sc, rw, start, cnt, tmin, tmax, res)) return;
@@ -147,8 +147,8 @@ __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, flo
         const float bound = MODE == MODE_CLOSEST ? __double2float_ru(res.t) : rd.w;
         if (!(cur & kLeafFlag)) {
             NodeHits h;
-            const int m = node_test4<true>(sc.nodes + cur, rb, ro.w, bound, h);
-            cur = descend(m, h, saddr, ovf, sp, bound);
+            node_test4<true>(sc.nodes + cur, rb, ro.w, bound, h);
+            cur = descend(h, saddr, ovf, sp, bound);
         } else {
             uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
             if (process_tris64<MODE>(sc, o, d, start, cnt, tmin, tmax, res)) return;
