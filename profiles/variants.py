@@ -9,13 +9,10 @@ VDIR = os.path.join(ROOT, "pyrenderer_b200", "variants")
 # -6 %, PRMT+FADD byte->float instead of I2F.U8 -8 %, L1 prefetch of the far child 0 %, smem stack
 # depth 8/12/16 no effect -- none of them is in the tree any more; add -D switches here to try new ones.
 VARIANTS = {
-    "n8": ("-DPRT_POP_LAZY=0", "-DPRT_MIN_BLOCKS=8"),
-    "n8q1": ("-DPRT_POP_LAZY=0", "-DPRT_MIN_BLOCKS=8", "-DPRT_QCONV_AXES=1"),
-    "n8q2": ("-DPRT_POP_LAZY=0", "-DPRT_MIN_BLOCKS=8", "-DPRT_QCONV_AXES=2"),
-    "n8q3": ("-DPRT_POP_LAZY=0", "-DPRT_MIN_BLOCKS=8", "-DPRT_QCONV_AXES=3"),
-    "n8q2v2": ("-DPRT_POP_LAZY=0", "-DPRT_MIN_BLOCKS=8", "-DPRT_QCONV_AXES=2", "-DPRT_VISITS_PER_ITER=2"),
-    "n8q2v4": ("-DPRT_POP_LAZY=0", "-DPRT_MIN_BLOCKS=8", "-DPRT_QCONV_AXES=2", "-DPRT_VISITS_PER_ITER=4"),
-    "l8q2v4": ("-DPRT_POP_LAZY=1", "-DPRT_MIN_BLOCKS=8", "-DPRT_QCONV_AXES=2", "-DPRT_VISITS_PER_ITER=4"),
+    "base": (),
+    "inl": ("-DPRT_SPILL_INL=__forceinline__",),
+    "slowrcp": ("-DPRT_SLOW_RCP",),
+    "inl_slowrcp": ("-DPRT_SPILL_INL=__forceinline__", "-DPRT_SLOW_RCP"),
 }
 if sys.argv[1] == "build":
     from pyrenderer_b200 import build

@@ -23,7 +23,7 @@ namespace prt {
 
 constexpr int kMaxStack = 128;  // the builder guarantees 3 * depth + 1 <= kMaxStack
 constexpr int kPStack = 16;     // levels kept in shared memory; deeper ones in local memory
-constexpr int kPStackOvf = kMaxStack - kPStack;
+constexpr int kPStackOvf = kMaxStack + 1;  // local-memory spill area: [0].x = spilled count, entries from [1]
 constexpr uint32_t kDone = kNoChild;  // has kLeafFlag set
 
 __device__ __forceinline__ float clamp_dir(float d) {
@@ -44,6 +44,18 @@ __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
     return r;
 }
 
+__device__ __forceinline__ RayBox make_raybox_fast(float3 o, float3 d) {  // persist.cuh: see rcp_fast
+    RayBox r;
+    r.o = o;
+#ifdef PRT_SLOW_RCP
+    r.idir = make_float3(__fdiv_rn(1.0f, clamp_dir(d.x)), __fdiv_rn(1.0f, clamp_dir(d.y)), __fdiv_rn(1.0f, clamp_dir(d.z)));
+#else
+    r.idir = make_float3(rcp_fast(clamp_dir(d.x)), rcp_fast(clamp_dir(d.y)), rcp_fast(clamp_dir(d.z)));
+#endif
+    r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
+    return r;
+}
+
 __device__ __forceinline__ float qf(uint32_t w, int byte) {
     return (float)((w >> (8 * byte)) & 0xffu);  // I2F.U8 with a static byte selector
 }
@@ -55,9 +67,26 @@ __device__ __forceinline__ float qf(uint32_t w, int byte) {
 #ifndef PRT_LDG256
 #define PRT_LDG256 1
 #endif
+#ifndef PRT_L2_HINT
+#define PRT_L2_HINT 0  // 1: BVH loads carry an L2 evict_last policy (rays / hits stream through evict-first)
+#endif
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+#if PRT_L2_HINT
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+#endif
+}
+// streaming (evict-first) 256-bit load of one 32-byte ray record: one sector, one request
+__device__ __forceinline__ void ldg256_cs(const void* p, float4& a, float4& b) {
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }
 __device__ __forceinline__ void ldg_node(const Node64* __restrict__ node, uint4& w0, uint4& w1, uint4& w2, uint4& w3) {
@@ -68,6 +97,24 @@ __device__ __forceinline__ void ldg_node(const Node64* __restrict__ node, uint4&
     const uint4* np = reinterpret_cast<const uint4*>(node);
     w0 = __ldg(np); w1 = __ldg(np + 1); w2 = __ldg(np + 2); w3 = __ldg(np + 3);
 #endif
+}
+
+// triangle fetch: leaf order = one 256-bit + one 64-bit load; BRUTE = global-id order, 3 x float4
+template <bool BRUTE>
+__device__ __forceinline__ void load_tri(const SceneDev& sc, uint32_t i, float3& p0, float3& p1, float3& p2, int& gid) {
+    if (BRUTE) {
+        const float4* tp = sc.tris + 3ull * i;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        p0 = xyz(a); p1 = xyz(b); p2 = xyz(c); gid = __float_as_int(a.w);
+    } else {
+        uint4 a, b;
+        ldg256(sc.tri_a + 2ull * i, a, b);
+        const float2 c = __ldg(sc.tri_b + i);
+        p0 = make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+        p1 = make_float3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+        p2 = make_float3(__uint_as_float(b.z), __uint_as_float(b.w), c.x);
+        gid = __float_as_int(c.y);
+    }
 }
 
 struct NodeHits {
@@ -127,36 +174,68 @@ __device__ __forceinline__ void node_test4(const Node64* __restrict__ node, cons
 }
 
 // ---- per-lane stack of (child reference, entry distance) pairs -----------------------
-// kPStack levels in shared memory ([level][lane] of 8-byte slots, conflict-free), deeper
-// levels in local memory.  Keeping the entry distance lets a pop discard, without touching
-// memory, every subtree that a closer hit found in the meantime has made irrelevant.
+// The top kPStack levels live in shared memory ([level][lane] of 8-byte slots, conflict-free).
+// Hot paths never test for overflow: a push that finds fewer than three free levels first
+// SPILLS the bottom kSpill levels to a local-memory array (and shifts the rest down), a pop that
+// finds the shared part empty UNSPILLS kSpill levels -- both rare, out-of-line in effect.  The
+// spilled count lives in ovf[0].x (local memory, not a register).  Keeping the entry distance
+// lets a pop discard, without touching memory, every subtree that a closer hit found in the
+// meantime has made irrelevant.
+constexpr int kSpill = kPStack / 2;
+#ifndef PRT_SPILL_INL
+#define PRT_SPILL_INL __forceinline__  // a real call costs 4 % (ABI constraints on the hot loop)
+#endif
+constexpr uint32_t kStackStride = kTraceThreads * 8u;
+__device__ __forceinline__ void sstack_st(uint32_t saddr, int i, uint32_t ref, uint32_t tb) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)i * kStackStride), "r"(ref), "r"(tb) : "memory");
+}
+__device__ __forceinline__ void sstack_ld(uint32_t saddr, int i, uint32_t& ref, uint32_t& tb) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(saddr + (uint32_t)i * kStackStride) : "memory");
+}
+__device__ __forceinline__ void sstack_reset(uint2* ovf, int& sp) { sp = 0; ovf[0].x = 0u; }
+// (sp by value in and out: a reference parameter of a real call would pin sp to local memory)
+static __device__ PRT_SPILL_INL int sstack_spill(uint32_t saddr, uint2* ovf, int sp) {
+    const uint32_t n = ovf[0].x;
+    for (int i = 0; i < kSpill; ++i) {
+        uint32_t r, t;
+        sstack_ld(saddr, i, r, t);
+        ovf[1 + n + i] = make_uint2(r, t);
+    }
+    for (int i = kSpill; i < sp; ++i) {
+        uint32_t r, t;
+        sstack_ld(saddr, i, r, t);
+        sstack_st(saddr, i - kSpill, r, t);
+    }
+    ovf[0].x = n + kSpill;
+    return sp - kSpill;
+}
+static __device__ PRT_SPILL_INL int sstack_unspill(uint32_t saddr, uint2* ovf) {  // shared part empty; returns the new sp
+    const uint32_t n = ovf[0].x;
+    if (n == 0u) return 0;
+    for (int i = 0; i < kSpill; ++i) {
+        const uint2 e = ovf[1 + n - kSpill + i];
+        sstack_st(saddr, i, e.x, e.y);
+    }
+    ovf[0].x = n - kSpill;
+    return kSpill;
+}
 __device__ __forceinline__ void sstack_push(uint32_t saddr, uint2* ovf, int& sp, uint32_t ref, float t) {
-    if (sp < kPStack)
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)), "r"(ref), "r"(__float_as_uint(t)) : "memory");
-    else
-        ovf[sp - kPStack] = make_uint2(ref, __float_as_uint(t));
+    if (sp >= kPStack) sp = sstack_spill(saddr, ovf, sp);
+    sstack_st(saddr, sp, ref, __float_as_uint(t));
     ++sp;
 }
-__device__ __forceinline__ uint32_t sstack_pop(uint32_t saddr, const uint2* ovf, int& sp, float& t) {
-    --sp;
-    uint32_t ref, tb;
-    if (sp < kPStack) {
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)) : "memory");
-    } else {
-        uint2 e = ovf[sp - kPStack];
-        ref = e.x; tb = e.y;
-    }
-    t = __uint_as_float(tb);
-    return ref;
-}
 // pop until an entry that can still beat `bound` (or the stack is empty -> kDone)
-__device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, const uint2* ovf, int& sp, float bound) {
-    while (sp > 0) {
-        float t;
-        const uint32_t ref = sstack_pop(saddr, ovf, sp, t);
-        if (t <= bound) return ref;
+__device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, uint2* ovf, int& sp, float bound) {
+    while (true) {
+        if (sp == 0) {
+            sp = sstack_unspill(saddr, ovf);
+            if (sp == 0) return kDone;
+        }
+        --sp;
+        uint32_t ref, tb;
+        sstack_ld(saddr, sp, ref, tb);
+        if (__uint_as_float(tb) <= bound) return ref;
     }
-    return kDone;
 }
 
 __device__ __forceinline__ void cswap(float& ta, uint32_t& ra, float& tb, uint32_t& rb) {
@@ -180,26 +259,16 @@ __device__ __forceinline__ void sort_hits(NodeHits& h) {
 #endif
 }
 
-#ifndef PRT_PUSH_UNCOND
-#define PRT_PUSH_UNCOND 1
-#endif
-// push the (sorted) hits 3, 2, 1.  Common case (three free shared-memory levels): three
-// unconditional stores, the stack pointer advances only past the valid ones -- no branch per child.
+// push the (sorted) hits 3, 2, 1: three unconditional stores, the stack pointer advances only
+// past the valid ones -- no branch per child.
 __device__ __forceinline__ void push_far(const NodeHits& h, uint32_t saddr, uint2* ovf, int& sp) {
     const float inf = __int_as_float(0x7f800000);
-#if PRT_PUSH_UNCOND
-    if (sp <= kPStack - 3) {
+    if (sp > kPStack - 3) sp = sstack_spill(saddr, ovf, sp);
 #pragma unroll
-        for (int c = 3; c >= 1; --c) {
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)sp * (kTraceThreads * 8u)), "r"(h.ref[c]), "r"(__float_as_uint(h.t[c])) : "memory");
-            sp += h.t[c] < inf ? 1 : 0;
-        }
-        return;
+    for (int c = 3; c >= 1; --c) {
+        sstack_st(saddr, sp, h.ref[c], __float_as_uint(h.t[c]));
+        sp += h.t[c] < inf ? 1 : 0;
     }
-#endif
-    if (h.t[3] < inf) sstack_push(saddr, ovf, sp, h.ref[3], h.t[3]);
-    if (h.t[2] < inf) sstack_push(saddr, ovf, sp, h.ref[2], h.t[2]);
-    if (h.t[1] < inf) sstack_push(saddr, ovf, sp, h.ref[1], h.t[1]);
 }
 
 __device__ __forceinline__ uint32_t descend(NodeHits& h, uint32_t saddr, uint2* ovf, int& sp, float bound) {
@@ -208,23 +277,6 @@ __device__ __forceinline__ uint32_t descend(NodeHits& h, uint32_t saddr, uint2* 
     push_far(h, saddr, ovf, sp);
     if (!(h.t[0] < inf)) return sstack_pop_live(saddr, ovf, sp, bound);
     return h.ref[0];
-}
-
-// Loop-free variant for the persistent traversal: a miss returns kRetry and the caller pops ONE
-// entry at its next visit slot (pop_once); a culled entry costs the lane that slot instead of
-// making the whole warp wait in a 3-lane pop loop.
-constexpr uint32_t kRetry = 0xFFFFFFFEu;  // has kLeafFlag set; not a valid leaf reference
-__device__ __forceinline__ uint32_t descend_lazy(NodeHits& h, uint32_t saddr, uint2* ovf, int& sp) {
-    const float inf = __int_as_float(0x7f800000);
-    sort_hits(h);
-    push_far(h, saddr, ovf, sp);
-    return h.t[0] < inf ? h.ref[0] : kRetry;
-}
-__device__ __forceinline__ uint32_t pop_once(uint32_t saddr, const uint2* ovf, int& sp, float bound) {
-    if (sp <= 0) return kDone;
-    float t;
-    const uint32_t ref = sstack_pop(saddr, ovf, sp, t);
-    return t <= bound ? ref : kRetry;
 }
 
 }  // namespace prt

@@ -274,10 +274,19 @@ __device__ __forceinline__ bool quant_planes(float o, float scale, float lo, flo
     return fmaf((float)a, scale, o) <= lo && fmaf((float)b, scale, o) >= hi;
 }
 
+// leaf-order triangle record (common.cuh): 32 B (p0.xyz, p1.xyz, p2.xy) + 8 B (p2.z, global id)
+__device__ __forceinline__ void write_tri(const float4* __restrict__ verts, uint32_t t, uint32_t k, uint4* out_a,
+                                          float2* out_b) {
+    const float4 a = verts[3ull * t], b = verts[3ull * t + 1], c = verts[3ull * t + 2];
+    out_a[2ull * k] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(b.x));
+    out_a[2ull * k + 1] = make_uint4(__float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(c.x), __float_as_uint(c.y));
+    out_b[k] = make_float2(c.z, a.w);
+}
+
 __device__ __forceinline__ void write_leaf_tris(const float4* __restrict__ verts,
                                                 const uint32_t* __restrict__ vals, const int* left,
                                                 const int* right, int n, int x, uint32_t start,
-                                                float4* out) {
+                                                uint4* out_a, float2* out_b) {
     int stack[16];
     int sp = 0;
     uint32_t k = start;
@@ -285,9 +294,7 @@ __device__ __forceinline__ void write_leaf_tris(const float4* __restrict__ verts
     while (true) {
         if (cur >= n - 1) {
             uint32_t t = vals[cur - (n - 1)];
-            out[3ull * k] = verts[3ull * t];
-            out[3ull * k + 1] = verts[3ull * t + 1];
-            out[3ull * k + 2] = verts[3ull * t + 2];
+            write_tri(verts, t, k, out_a, out_b);
             ++k;
             if (sp == 0) break;
             cur = stack[--sp];
@@ -318,7 +325,8 @@ struct EmitArgs {
     unsigned int* queue_tail;
     unsigned int* tri_tail;
     Node64* nodes;
-    float4* tris_out;
+    uint4* tri_a;
+    float2* tri_b;
 };
 
 __device__ __forceinline__ void write_record(Node64* out, const float o[3], const float ext[3],
@@ -404,7 +412,7 @@ __global__ void emit4_kernel(EmitArgs A, const unsigned int* __restrict__ level)
         chi[k][0] = h.x; chi[k][1] = h.y; chi[k][2] = h.z;
         if (leaf[k]) {
             const uint32_t cnt = A.tcount[c];
-            write_leaf_tris(A.verts, A.vals, A.left, A.right, n, c, start, A.tris_out);
+            write_leaf_tris(A.verts, A.vals, A.left, A.right, n, c, start, A.tri_a, A.tri_b);
             ref[k] = kLeafFlag | (start << 3) | cnt;
             start += cnt;
         } else {
@@ -416,7 +424,7 @@ __global__ void emit4_kernel(EmitArgs A, const unsigned int* __restrict__ level)
 }
 
 // n == 1: one record whose only child is the only triangle
-__global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nodes, float4* tris_out) {
+__global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nodes, uint4* tri_a, float2* tri_b) {
     float3 lo, hi;
     tri_box(verts, 0, lo, hi);
     const float o[3] = {lo.x, lo.y, lo.z};
@@ -426,7 +434,7 @@ __global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nod
     chi[0][0] = hi.x; chi[0][1] = hi.y; chi[0][2] = hi.z;
     const uint32_t ref[4] = {kLeafFlag | 1u, kNoChild, kNoChild, kNoChild};
     write_record(nodes, o, ext, clo, chi, ref, 1);
-    tris_out[0] = verts[0]; tris_out[1] = verts[1]; tris_out[2] = verts[2];
+    write_tri(verts, 0, 0, tri_a, tri_b);
 }
 
 }  // namespace
@@ -447,7 +455,8 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     const int n = (int)nt;
     *too_deep = false;
     cudaFree(ctx->nodes); ctx->nodes = nullptr;
-    cudaFree(ctx->tris_leaf); ctx->tris_leaf = nullptr;
+    cudaFree(ctx->tri_a); ctx->tri_a = nullptr;
+    cudaFree(ctx->tri_b); ctx->tri_b = nullptr;
     ctx->n_nodes = 0;
     ctx->bvh_built = false;
     prt_bvh_stats st = {};
@@ -462,7 +471,8 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     cudaEvent_t ev[7];
     for (auto& e : ev) cudaEventCreate(&e);
     const size_t nn = 2 * (size_t)nt - 1;
-    BUILD_TRY(cudaMalloc(&ctx->tris_leaf, sizeof(float4) * 3 * (size_t)nt));
+    BUILD_TRY(cudaMalloc(&ctx->tri_a, sizeof(uint4) * 2 * (size_t)nt));
+    BUILD_TRY(cudaMalloc(&ctx->tri_b, sizeof(float2) * (size_t)nt));
     BUILD_TRY(cudaMalloc(&B.scene_box, 6 * sizeof(int)));
     BUILD_TRY(cudaMalloc(&B.max_depth, sizeof(unsigned int)));
     BUILD_TRY(cudaMemset(B.max_depth, 0, sizeof(unsigned int)));
@@ -528,7 +538,7 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         A.verts = ctx->verts_gid; A.vals = B.vals[sorted]; A.left = B.left; A.right = B.right;
         A.bmin = B.bmin; A.bmax = B.bmax; A.tcount = B.tcount; A.collapsed = B.collapsed; A.n = n;
         A.queue = B.queue; A.queue_tail = B.tails; A.tri_tail = B.tails + 1; A.nodes = ctx->nodes;
-        A.tris_out = ctx->tris_leaf;
+        A.tri_a = ctx->tri_a; A.tri_b = ctx->tri_b;
         // One launch per level, driven from the device (no host round trip per level): a level has
         // at most n_rec records and the tree at most kMaxStack/3 levels that traversal can use.
         // Levels shrink/grow by <= 4x, so the grid is sized from the previous bound.
@@ -546,7 +556,7 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         depth = fin[4];
         if (fin[2] < fin[3]) depth = kMaxStack;  // levels left over: deeper than traversal supports
     } else {
-        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tris_leaf);
+        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tri_a, ctx->tri_b);
         depth = 1;
     }
     cudaEventRecord(ev[6]);

@@ -13,10 +13,13 @@ constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kNoChild = 0xFFFFFFFFu;   // absent child slot; also the "traversal finished" marker
 
 // ---- device scene ---------------------------------------------------------
-// Triangles live in HBM as 3 x float4 (48 B), in BVH leaf (DFS) order so that a
-// leaf's triangles are contiguous:  (p0.xyz, bits(global id)), (p1.xyz,
-// bits(material)), (p2.xyz, 0).  Shading data (normal + material) is a separate
-// float4 array indexed by the GLOBAL id, touched once per path vertex only.
+// Traversal reads triangles in BVH leaf order (a leaf's triangles are contiguous) from two
+// arrays: 32 B (p0.xyz, p1.xyz, p2.xy) + 8 B (p2.z, bits(global id)) -- 40 B and exactly two
+// L1 sectors per test (the former 3 x float4 record cost three: the data pipe moves one
+// 32-byte sector per cycle for divergent lanes, and that pipe is what bounds the traversal).
+// The global-id-order copy (3 x float4: (p0, bits(gid)), (p1, bits(material)), (p2, 0)) serves
+// brute force, light sampling and hit-point reconstruction.  Shading data (normal + material)
+// is a separate float4 array indexed by the GLOBAL id, touched once per path vertex only.
 // 4-wide BVH node, 64 B = four float4 = two 32-byte sectors: 16 B per child box + reference,
 // the same bytes-per-child as a 32-byte 2-wide node (see DESIGN.md 2 for why 4-wide).
 struct Node64 {
@@ -28,7 +31,9 @@ struct Node64 {
 static_assert(sizeof(Node64) == 64, "node must be 64 bytes");
 
 struct SceneDev {
-    const float4* tris;      // [nt*3] leaf order
+    const float4* tris;      // [nt*3] GLOBAL-id order, 3 x float4 (brute-force modes only)
+    const uint4* tri_a;      // [nt*2] leaf order, 32 B: p0.xyz, p1.xyz, p2.xy   (one LDG.256 = one sector)
+    const float2* tri_b;     // [nt]   leaf order,  8 B: p2.z, bits(global id)
     const Node64* nodes;     // [n_nodes]
     const float4* shade;     // [nt] by global id: normal.xyz, bits(material)
     const prt_material* mats;

@@ -20,7 +20,8 @@ struct prt_ctx {
     bool scene_set = false;
 
     // BVH (device)
-    float4* tris_leaf = nullptr;   // [nt*3] leaf order, w carries gid / material
+    uint4* tri_a = nullptr;        // [nt*2] leaf order: p0.xyz, p1.xyz, p2.xy
+    float2* tri_b = nullptr;       // [nt]   leaf order: p2.z, bits(global id)
     prt::Node64* nodes = nullptr;
     uint32_t n_nodes = 0;
     bool bvh_built = false;
@@ -60,7 +61,9 @@ struct prt_ctx {
 
     prt::SceneDev scene_dev() const {
         prt::SceneDev s;
-        s.tris = bvh_built ? tris_leaf : nullptr;
+        s.tris = verts_gid;
+        s.tri_a = bvh_built ? tri_a : nullptr;
+        s.tri_b = bvh_built ? tri_b : nullptr;
         s.nodes = nodes;
         s.shade = shade;
         s.mats = mats;

@@ -25,10 +25,6 @@
 #define PRT_VISITS_PER_ITER 3  // record visits between two rounds of warp votes (profiles/r1_sweeps.txt)
 #endif
 
-#ifndef PRT_POP_LAZY
-#define PRT_POP_LAZY 0  // 1: one predicated pop per visit slot instead of the pop loop (measured: -1 % soup, -12 % Cornell)
-#endif
-
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 8  // __launch_bounds__ min blocks/SM of the persistent traversal kernels: caps ptxas at 64 registers
 #endif
@@ -81,10 +77,11 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     io.load(k, ro, rd, tag);
                     const float3 o = xyz(ro), d = xyz(rd);
                     rw = make_raywf(o, d);
-                    rb = make_raybox(o, d);
+                    rb = make_raybox_fast(o, d);
                     tmin = ro.w; tmax = rd.w;
                     bt = tmax; bu = 0.f; bv = 0.f; bgid = -1;
-                    cur = 0; sp = 0;
+                    cur = 0;
+                    sstack_reset(ovf, sp);
                     has_ray = true;
                     if (COUNT) ++c_rays;
                 }
@@ -101,38 +98,31 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
 #pragma unroll
         for (int rep = 0; rep < PRT_VISITS_PER_ITER; ++rep) {
             const float bound = MODE == MODE_CLOSEST ? bt : tmax;
-#if PRT_POP_LAZY
-            if (has_ray && cur == kRetry) cur = pop_once(saddr, ovf, sp, bound);
-#endif
             if (has_ray && !(cur & kLeafFlag)) {
                 if (COUNT) ++c_nodes;
                 NodeHits h;
                 node_test4<false>(sc.nodes + cur, rb, tmin, bound, h);
-#if PRT_POP_LAZY
-                cur = descend_lazy(h, saddr, ovf, sp);
-#else
                 cur = descend(h, saddr, ovf, sp, bound);
-#endif
             }
         }
 
         // ---- leaves: parked lanes go together
-        const bool at_leaf = has_ray && (cur & kLeafFlag) && cur < kRetry;
+        const bool at_leaf = has_ray && (cur & kLeafFlag) && cur != kDone;
         const unsigned leafm = __ballot_sync(FULL, at_leaf);
         // idle lanes keep cur == kDone, so "no leaf flag" == "still walking records"
-        const unsigned nodem = __ballot_sync(FULL, (cur & kLeafFlag) == 0u || cur == kRetry);  // kRetry: walking again after its pop
+        const unsigned nodem = ~__ballot_sync(FULL, (cur & kLeafFlag) != 0u);
         if (leafm && (__popc(leafm) >= sc.leaf_batch || nodem == 0)) {
             if (COUNT) { ++c_lphases; c_llanes += __popc(leafm); }
             if (at_leaf) {
                 const uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
                 bool stop = false;
                 for (uint32_t k = 0; k < cnt; ++k) {
-                    const float4* tp = sc.tris + 3ull * (start + k);
-                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    float3 p0, p1, p2;
+                    int gid;
+                    load_tri<false>(sc, start + k, p0, p1, p2, gid);
                     if (COUNT) ++c_tris;
                     TriHit h;
-                    if (tri_watertight_fast(rw, xyz(a), xyz(b), xyz(c), tmin, MODE == MODE_CLOSEST ? bt : tmax, h)) {
-                        const int gid = __float_as_int(a.w);
+                    if (tri_watertight_fast(rw, p0, p1, p2, tmin, MODE == MODE_CLOSEST ? bt : tmax, h)) {
                         if (MODE == MODE_CLOSEST) {
                             if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; }
                         } else {
@@ -141,11 +131,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                         }
                     }
                 }
-#if PRT_POP_LAZY
-                cur = stop ? kDone : kRetry;
-#else
                 cur = stop ? kDone : sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? bt : tmax);
-#endif
             }
         }
         if (has_ray && cur == kDone) {

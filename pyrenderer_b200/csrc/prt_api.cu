@@ -42,9 +42,9 @@ __global__ void pack_shade_kernel(const float* __restrict__ v, const float* __re
 
 static void free_scene(prt_ctx* c) {
     cudaFree(c->verts_gid); cudaFree(c->shade); cudaFree(c->mats); cudaFree(c->light_tris);
-    cudaFree(c->tris_leaf); cudaFree(c->nodes);
+    cudaFree(c->tri_a); cudaFree(c->tri_b); cudaFree(c->nodes);
     c->verts_gid = nullptr; c->shade = nullptr; c->mats = nullptr; c->light_tris = nullptr;
-    c->tris_leaf = nullptr; c->nodes = nullptr;
+    c->tri_a = nullptr; c->tri_b = nullptr; c->nodes = nullptr;
     c->nt = c->nm = c->nl = c->n_nodes = 0;
     c->scene_set = false; c->bvh_built = false;
 }

@@ -74,10 +74,15 @@ template <int MODE>
 struct ApiIO {
     const float4* rays;
     void* out;
+    bool aligned32;  // ray array on a 32-byte boundary (any cudaMalloc'd / torch buffer): one 256-bit load per ray
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         // rays and hits stream through once: evict-first, so they do not push the BVH out of L2
-        ro = __ldcs(rays + 2ull * k);
-        rd = __ldcs(rays + 2ull * k + 1);
+        if (aligned32) {
+            ldg256_cs(rays + 2ull * k, ro, rd);
+        } else {
+            ro = __ldcs(rays + 2ull * k);
+            rd = __ldcs(rays + 2ull * k + 1);
+        }
         tag = k;
     }
     __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out,
                         unsigned int* fetch, Counters* ctr) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
-    ApiIO<MODE> io{rays, out};
+    ApiIO<MODE> io{rays, out, (reinterpret_cast<uintptr_t>(rays) & 31u) == 0u};
     trace_persistent<MODE, COUNT>(sc, io, fetch, n, &s_stack[0][threadIdx.x], ctr);
 }
 
@@ -154,7 +159,6 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
     if (!ctx->scene_set) { ctx->set_error("trace: no scene (call prt_scene_set_triangles first)"); return PRT_ERR_STATE; }
     if (!brute && !ctx->bvh_built) { ctx->set_error("trace: BVH not built (call prt_bvh_build or pass PRT_TRACE_BRUTE)"); return PRT_ERR_STATE; }
     SceneDev sc = ctx->scene_dev();
-    if (brute) sc.tris = ctx->verts_gid;
     if (exact && ctx->flag_cap < n) {
         if (ctx->flag_list) cudaFree(ctx->flag_list);
         ctx->flag_list = nullptr; ctx->flag_cap = 0;

@@ -17,20 +17,20 @@ struct TraceResult {
     uint32_t n_nodes, n_tris;  // COUNT
 };
 
-template <int MODE, bool EXACT, bool COUNT>
+template <int MODE, bool EXACT, bool COUNT, bool BRUTE>
 __device__ __forceinline__ bool process_tris(const SceneDev& sc, const RayW& rw, uint32_t start,
                                              uint32_t cnt, float tmin, float tmax,
                                              TraceResult& res) {
     for (uint32_t k = 0; k < cnt; ++k) {
-        const float4* tp = sc.tris + 3ull * (start + k);
-        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-        int gid = __float_as_int(a.w);
+        float3 p0, p1, p2;
+        int gid;
+        load_tri<BRUTE>(sc, start + k, p0, p1, p2, gid);
         if (COUNT) ++res.n_tris;
         TriHit h;
         bool unc = false;
         float bound = MODE == MODE_CLOSEST ? res.t : tmax;
         float berr = MODE == MODE_CLOSEST ? res.dt : 0.0f;
-        int hit = tri_watertight<EXACT>(rw, xyz(a), xyz(b), xyz(c), tmin, bound, berr, h, unc);
+        int hit = tri_watertight<EXACT>(rw, p0, p1, p2, tmin, bound, berr, h, unc);
         if (EXACT && unc) { res.uncertain = true; return true; }
         if (!hit) continue;
         if (MODE == MODE_CLOSEST) {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 
     if (BRUTE) {
         for (uint32_t s = 0; s < sc.nt; s += 4096u) {
             uint32_t c = min(4096u, sc.nt - s);
-            if (process_tris<MODE, EXACT, COUNT>(sc, rw, s, c, tmin, tmax, res)) return;
+            if (process_tris<MODE, EXACT, COUNT, true>(sc, rw, s, c, tmin, tmax, res)) return;
         }
         return;
     }
@@ -69,7 +69,8 @@ __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 
     RayBox rb = make_raybox(o, d);
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
     uint2 ovf[kPStackOvf];
-    int sp = 0;
+    int sp;
+    sstack_reset(ovf, sp);
     uint32_t cur = 0;
     while (cur != kDone) {
         // EXACT: a candidate closer than best + its error bound must still be visited
@@ -81,7 +82,7 @@ __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 
             cur = descend(h, saddr, ovf, sp, bound);
         } else {
             uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
-            if (process_tris<MODE, EXACT, COUNT>(sc, rw, start, cnt, tmin, tmax, res)) return;
+            if (process_tris<MODE, EXACT, COUNT, false>(sc, rw, start, cnt, tmin, tmax, res)) return;
             cur = sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? res.t + (EXACT ? res.dt : 0.0f) : tmax);
         }
     }
@@ -98,17 +99,17 @@ struct TraceResult64 {
     unsigned long long sum;
 };
 
-template <int MODE>
+template <int MODE, bool BRUTE>
 __device__ __forceinline__ bool process_tris64(const SceneDev& sc, const double* o, const double* d,
                                                uint32_t start, uint32_t cnt, double tmin,
                                                double tmax, TraceResult64& res) {
     for (uint32_t k = 0; k < cnt; ++k) {
-        const float4* tp = sc.tris + 3ull * (start + k);
-        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-        int gid = __float_as_int(a.w);
+        float3 p0, p1, p2;
+        int gid;
+        load_tri<BRUTE>(sc, start + k, p0, p1, p2, gid);
         double t, u, v;
         double bound = MODE == MODE_CLOSEST ? res.t : tmax;
-        if (!mt_f64(xyz(a), xyz(b), xyz(c), o, d, tmin, bound, t, u, v)) continue;
+        if (!mt_f64(p0, p1, p2, o, d, tmin, bound, t, u, v)) continue;
         if (MODE == MODE_CLOSEST) {
             if (t < res.t || gid < res.gid || res.gid < 0) { res.t = t; res.u = u; res.v = v; res.gid = gid; }
         } else if (MODE == MODE_ANY) {
@@ -132,7 +133,7 @@ __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, flo
     if (BRUTE) {
         for (uint32_t s = 0; s < sc.nt; s += 4096u) {
             uint32_t c = min(4096u, sc.nt - s);
-            if (process_tris64<MODE>(sc, o, d, s, c, tmin, tmax, res)) return;
+            if (process_tris64<MODE, true>(sc, o, d, s, c, tmin, tmax, res)) return;
         }
         return;
     }
@@ -140,7 +141,8 @@ __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, flo
     RayBox rb = make_raybox(xyz(ro), xyz(rd));
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
     uint2 ovf[kPStackOvf];
-    int sp = 0;
+    int sp;
+    sstack_reset(ovf, sp);
     uint32_t cur = 0;
     while (cur != kDone) {
         // box culling stays FP32 but conservative: bound rounded up, intervals widened (EXACT)
@@ -151,7 +153,7 @@ __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, flo
             cur = descend(h, saddr, ovf, sp, bound);
         } else {
             uint32_t start = (cur & ~kLeafFlag) >> 3, cnt = cur & 7u;
-            if (process_tris64<MODE>(sc, o, d, start, cnt, tmin, tmax, res)) return;
+            if (process_tris64<MODE, false>(sc, o, d, start, cnt, tmin, tmax, res)) return;
             cur = sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? __double2float_ru(res.t) : rd.w);
         }
     }

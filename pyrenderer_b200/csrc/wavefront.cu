@@ -146,8 +146,7 @@ struct QueueClosestIO {
     const uint32_t* queue;
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         tag = queue[k];
-        ro = rays[2 * (size_t)tag];
-        rd = rays[2 * (size_t)tag + 1];
+        ldg256_cs(rays + 2 * (size_t)tag, ro, rd);  // wave buffers are cudaMalloc'd: 32-byte aligned
     }
     __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
         hits[tag] = make_float4(t, u, v, __int_as_float(gid));
@@ -169,8 +168,7 @@ struct QueueShadowIO {
     float4* L;
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         tag = k;
-        ro = srays[2 * (size_t)k];
-        rd = srays[2 * (size_t)k + 1];
+        ldg256_cs(srays + 2 * (size_t)k, ro, rd);
     }
     __device__ __forceinline__ void store(uint32_t tag, float, float, float, int gid) const {
         if (gid < 0) {
