@@ -231,8 +231,9 @@ def main():
     c = ctx.counters()
     n_node = c["node_visits"] / RAYS_PER_BATCH
     n_tri = c["tri_tests"] / RAYS_PER_BATCH
-    # SURVEY 8d per-ray figure with the real fetch size of a (4-wide, 64-byte) node record
-    bytes_per_ray = 48.0 + 64.0 * n_node + 48.0 * n_tri
+    # SURVEY 8d per-ray figure with the real fetch sizes: 32 B ray in + 16 B hit out, 64 B per
+    # (4-wide) node record visited, 40 B per triangle tested (32 + 8 byte leaf-order record)
+    bytes_per_ray = 48.0 + 64.0 * n_node + 40.0 * n_tri
     hit_frac = float((hits[:, 3].view(torch.int32) >= 0).float().mean().item())
 
     clk = ClockSampler(local).start()

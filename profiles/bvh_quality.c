@@ -131,6 +131,34 @@ static int collapse(int root) { /* BFS */
     }
     n_wide = qt; free(q); return 0;
 }
+/* SAH-optimal 4-wide collapse (dynamic programme of Ylitie, Karras, Laine 2017, sect. 3.1) */
+static float (*Cst)[4]; static unsigned char (*Dec)[4]; /* Dec[n][k-1]: 0 = n stays one child; i>0 = dissolved, left gets i slots */
+static float CT = 1.0f;
+static void dp_rec(int n) {
+    if (nodes[n].tri >= 0) { for (int k = 0; k < 4; ++k) { Cst[n][k] = area(&nodes[n].b) * CT; Dec[n][k] = 0; } return; }
+    int l = nodes[n].left, r = nodes[n].right; dp_rec(l); dp_rec(r);
+    float D[5]; unsigned char Di[5];
+    for (int k = 2; k <= 4; ++k) { D[k] = 3e38f; Di[k] = 1; for (int i = 1; i < k; ++i) { float c = Cst[l][i - 1] + Cst[r][k - i - 1]; if (c < D[k]) { D[k] = c; Di[k] = (unsigned char)i; } } }
+    Cst[n][0] = area(&nodes[n].b) + D[4]; Dec[n][0] = 0;
+    for (int k = 2; k <= 4; ++k) { if (D[k] < Cst[n][0]) { Cst[n][k - 1] = D[k]; Dec[n][k - 1] = Di[k]; } else { Cst[n][k - 1] = Cst[n][0]; Dec[n][k - 1] = 0; } }
+}
+static int gather(int n, int k, int* out, int cnt) { /* children of a wide node: n may use k slots */
+    if (nodes[n].tri >= 0 || Dec[n][k - 1] == 0) { out[cnt++] = n; return cnt; }
+    int i = Dec[n][k - 1]; cnt = gather(nodes[n].left, i, out, cnt); return gather(nodes[n].right, k - i, out, cnt);
+}
+static void collapse_dp(int root) {
+    Cst = malloc(sizeof(float) * 4 * n_nodes); Dec = malloc(4 * n_nodes); dp_rec(root);
+    int* q = malloc(sizeof(int) * (N + 1)); int qh = 0, qt = 0; q[qt++] = root;
+    while (qh < qt) {
+        int bn = q[qh]; WNode* w = &wn[qh]; ++qh; int ch[4]; int n = 0;
+        /* the node itself is dissolved with 4 slots: best split of D[4] */
+        { int l = nodes[bn].left, r = nodes[bn].right; float best = 3e38f; int bi = 1; for (int i = 1; i < 4; ++i) { float c = Cst[l][i - 1] + Cst[r][4 - i - 1]; if (c < best) { best = c; bi = i; } }
+          n = gather(l, bi, ch, n); n = gather(r, 4 - bi, ch, n); }
+        w->nch = n;
+        for (int i = 0; i < n; ++i) { w->cb[i] = nodes[ch[i]].b; if (nodes[ch[i]].tri >= 0) w->ref[i] = ~nodes[ch[i]].tri; else { w->ref[i] = qt; q[qt++] = ch[i]; } }
+    }
+    n_wide = qt; free(q); free(Cst); free(Dec);
+}
 static double sah_binary(int root) { double s = 0; float ra = area(&nodes[root].b); for (int i = 0; i < n_nodes; ++i) s += area(&nodes[i].b) / ra; return s; }
 static double sah_wide(void) { double s = 1.0; float ra = 0; Box r = empty_box(); for (int i = 0; i < wn[0].nch; ++i) grow(&r, &wn[0].cb[i]); ra = area(&r);
     for (int k = 0; k < n_wide; ++k) for (int i = 0; i < wn[k].nch; ++i) if (wn[k].ref[i] >= 0) s += area(&wn[k].cb[i]) / ra; return s; }
@@ -178,8 +206,10 @@ int main(int argc, char** argv) {
     nodes = malloc(sizeof(BNode) * 2 * N); wn = malloc(sizeof(WNode) * N);
     morton_sort();
     const char* which = argc > 4 ? argv[4] : "lbvh,sah,ploc8,ploc16";
-    if (strstr(which, "lbvh")) { n_nodes = 0; int root = lbvh_rec(0, N - 1); collapse(root); trace(rays, nr, "lbvh", sah_binary(root)); }
-    if (strstr(which, "sah")) { n_nodes = 0; idx = malloc(sizeof(int) * N); for (int i = 0; i < N; ++i) idx[i] = i; int root = sah_rec(0, N); collapse(root); trace(rays, nr, "sah", sah_binary(root)); }
+    if (strstr(which, "lbvh")) { n_nodes = 0; int root = lbvh_rec(0, N - 1); collapse(root); trace(rays, nr, "lbvh", sah_binary(root));
+        for (CT = 0.5f; CT <= 4.0f; CT *= 2.f) { char nm[32]; sprintf(nm, "lbvh-dp%.1f", CT); collapse_dp(root); trace(rays, nr, nm, sah_binary(root)); } }
+    if (strstr(which, "sah")) { n_nodes = 0; idx = malloc(sizeof(int) * N); for (int i = 0; i < N; ++i) idx[i] = i; int root = sah_rec(0, N); collapse(root); trace(rays, nr, "sah", sah_binary(root));
+        CT = 1.0f; collapse_dp(root); trace(rays, nr, "sah-dp1.0", sah_binary(root)); }
     for (int R = 4; R <= 64; R *= 2) { char nm[16]; sprintf(nm, "ploc%d", R); if (!strstr(which, nm)) continue; n_nodes = 0; int root = ploc_build(R); collapse(root); trace(rays, nr, nm, sah_binary(root)); }
     return 0;
 }

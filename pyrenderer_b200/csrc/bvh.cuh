@@ -126,9 +126,21 @@ struct NodeHits {
 // PRMT builds the float 1 + q * 2^-15 (0x3F80qq00) on the ALU pipe and the slab becomes
 // t = f * (a * 2^15) + (b - a * 2^15); the other axes use I2F.U8 (XU pipe, 1/4 rate).  Splitting
 // the 24 conversions of a visit between the two pipes keeps either from limiting issue.
+#ifndef PRT_FMA2
+#define PRT_FMA2 1
+#endif
 #ifndef PRT_QCONV_AXES
 #define PRT_QCONV_AXES 2  // profiles/r1_sweeps.txt: 0 -> 1666, 1 -> 1706, 2 -> 1724, 3 -> 1689 Mrays/s (soup-1M)
 #endif
+// Two planes per instruction: sm_100 packed FP32 (FFMA2, PTX fma.rn.f32x2) with the per-axis
+// constants broadcast to both halves -- 12 FFMA2 per visit instead of 24 FFMA.
+__device__ __forceinline__ void fma2_bcast(float q0, float q1, float a, float b, float& t0, float& t1) {
+    unsigned long long q, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(q0), "f"(q1));
+    asm("{\n\t.reg .b64 aa, bb;\n\tmov.b64 aa, {%2, %2};\n\tmov.b64 bb, {%3, %3};\n\tfma.rn.f32x2 %0, %1, aa, bb;\n\t}"
+        : "=l"(d) : "l"(q), "f"(a), "f"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(d));
+}
 template <bool FOLD>
 struct PlaneEval {
     float a, b;
@@ -136,9 +148,18 @@ struct PlaneEval {
         const float a0 = scale * idir, b0 = (origin - ro) * idir;
         if (FOLD) { a = a0 * 32768.0f; b = b0 - a; } else { a = a0; b = b0; }
     }
-    __device__ __forceinline__ float operator()(uint32_t w, int c) const {
-        if (FOLD) return fmaf(__uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t)(c << 4))), a, b);
-        return fmaf(qf(w, c), a, b);
+    __device__ __forceinline__ float q(uint32_t w, int c) const {  // byte c -> the float the FMA consumes
+        if (FOLD) return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t)(c << 4)));
+        return qf(w, c);
+    }
+    __device__ __forceinline__ void eval4(uint32_t w, float t[4]) const {  // the four children's planes of one word
+#if PRT_FMA2
+        fma2_bcast(q(w, 0), q(w, 1), a, b, t[0], t[1]);
+        fma2_bcast(q(w, 2), q(w, 3), a, b, t[2], t[3]);
+#else
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[c] = fmaf(q(w, c), a, b);
+#endif
     }
 };
 
@@ -162,10 +183,14 @@ __device__ __forceinline__ void node_test4(const Node64* __restrict__ node, cons
         m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(px.b) + 255.0f * fabsf(px.a), fabsf(py.b) + 255.0f * fabsf(py.a)),
                                   fabsf(pz.b) + 255.0f * fabsf(pz.a)));
     const float inf = __int_as_float(0x7f800000);
+    float xn[4], xf[4], yn[4], yf[4], zn[4], zf[4];
+    px.eval4(nx, xn); px.eval4(fx, xf);
+    py.eval4(ny, yn); py.eval4(fy, yf);
+    pz.eval4(nz, zn); pz.eval4(fz, zf);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        float tn = fmaxf(fmaxf(px(nx, c), py(ny, c)), fmaxf(pz(nz, c), tmin));
-        float tf = fminf(fminf(px(fx, c), py(fy, c)), fminf(pz(fz, c), tmax));
+        float tn = fmaxf(fmaxf(xn[c], yn[c]), fmaxf(zn[c], tmin));
+        float tf = fminf(fminf(xf[c], yf[c]), fminf(zf[c], tmax));
         if (EXACT) { tn -= m; tf += m; }
         // absent children carry inverted planes AND kNoChild: the planes alone are not proof
         // (255*a + b can round to b for a tiny record far away)

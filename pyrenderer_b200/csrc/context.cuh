@@ -45,8 +45,9 @@ struct prt_ctx {
     // device staging of the *_host entry points (grow-only, reused across calls)
     void* stage[2] = {nullptr, nullptr};
     size_t stage_bytes[2] = {0, 0};
-    cudaStream_t copy_stream[2] = {nullptr, nullptr};
-    cudaEvent_t copy_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kHostSlots = 4;  // chunks in flight in prt_trace_closest_host
+    cudaStream_t copy_stream[3] = {nullptr, nullptr, nullptr};  // upload, compute, download
+    cudaEvent_t copy_event[3 * kHostSlots] = {};                // per slot: uploaded, traced, downloaded
 
     // wavefront state (wavefront.cu)
     void* wf = nullptr;

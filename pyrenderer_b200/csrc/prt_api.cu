@@ -257,35 +257,46 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
     USE_DEVICE(ctx);
     if (n == 0) return PRT_OK;
     if (!rays_host || !hits_host) { ctx->set_error("trace_host: NULL buffer"); return PRT_ERR_INVALID; }
+    // Three streams (upload, trace, download) and kHostSlots staging slots: the upload of chunk
+    // i+1.., the trace of chunk i and the download of chunk i-1 overlap; traces never overlap each
+    // other (a persistent launch fills the GPU) and each copy engine sees a FIFO.
+    constexpr int S = prt_ctx::kHostSlots;
     const uint64_t chunk = 1ull << 21;
-    const uint64_t cap = n < 2 * chunk ? n : 2 * chunk;  // two chunks in flight
+    const uint64_t cap = n < S * chunk ? n : S * chunk;
     int rc = stage_reserve(ctx, 0, sizeof(prt_ray) * cap);
     if (rc == PRT_OK) rc = stage_reserve(ctx, 1, sizeof(prt_hit) * cap);
     if (rc != PRT_OK) return rc;
-    for (int k = 0; k < 2; ++k)
-        if (!ctx->copy_stream[k]) PRT_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream[k], cudaStreamNonBlocking));
+    for (auto& st : ctx->copy_stream)
+        if (!st) PRT_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& ev : ctx->copy_event)
+        if (!ev) PRT_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     prt_ray* dr = (prt_ray*)ctx->stage[0];
     prt_hit* dh = (prt_hit*)ctx->stage[1];
-    // EXACT shares one flag list per context -> keep exact launches on one stream
-    const bool serial = (flags & PRT_TRACE_EXACT) != 0;
+    cudaStream_t s_up = ctx->copy_stream[0], s_tr = ctx->copy_stream[1], s_down = ctx->copy_stream[2];
     uint64_t done = 0;
-    int slot = 0;
-    while (done < n) {
-        uint64_t m = n - done < chunk ? n - done : chunk;
-        cudaStream_t s = ctx->copy_stream[serial ? 0 : slot];
-        uint64_t off = (cap == n) ? done : (uint64_t)slot * chunk;
-        PRT_CUDA_TRY(ctx, cudaMemcpyAsync(dr + off, rays_host + done, sizeof(prt_ray) * m, cudaMemcpyHostToDevice, s));
-        rc = launch_trace(ctx, 0, (const float4*)(dr + off), m, dh + off, nullptr, flags, s);
+    for (uint64_t i = 0; done < n; ++i) {
+        const int slot = (int)(i % S);
+        cudaEvent_t uploaded = ctx->copy_event[3 * slot], traced = ctx->copy_event[3 * slot + 1],
+                    downloaded = ctx->copy_event[3 * slot + 2];
+        const uint64_t m = n - done < chunk ? n - done : chunk;
+        const uint64_t off = (cap == n) ? done : (uint64_t)slot * chunk;
+        if (i >= (uint64_t)S) PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_up, traced, 0));  // ray slot read by its last trace
+        PRT_CUDA_TRY(ctx, cudaMemcpyAsync(dr + off, rays_host + done, sizeof(prt_ray) * m, cudaMemcpyHostToDevice, s_up));
+        PRT_CUDA_TRY(ctx, cudaEventRecord(uploaded, s_up));
+        PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_tr, uploaded, 0));
+        if (i >= (uint64_t)S) PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_tr, downloaded, 0));  // hit slot drained
+        rc = launch_trace(ctx, 0, (const float4*)(dr + off), m, dh + off, nullptr, flags, s_tr);
         if (rc != PRT_OK) break;
-        PRT_CUDA_TRY(ctx, cudaMemcpyAsync(hits_host + done, dh + off, sizeof(prt_hit) * m, cudaMemcpyDeviceToHost, s));
+        PRT_CUDA_TRY(ctx, cudaEventRecord(traced, s_tr));
+        PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_down, traced, 0));
+        PRT_CUDA_TRY(ctx, cudaMemcpyAsync(hits_host + done, dh + off, sizeof(prt_hit) * m, cudaMemcpyDeviceToHost, s_down));
+        PRT_CUDA_TRY(ctx, cudaEventRecord(downloaded, s_down));
         done += m;
-        slot ^= 1;
     }
-    cudaError_t e0 = cudaStreamSynchronize(ctx->copy_stream[0]);
-    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream[1]);
+    cudaError_t e0 = cudaStreamSynchronize(s_up), e1 = cudaStreamSynchronize(s_tr), e2 = cudaStreamSynchronize(s_down);
     if (rc != PRT_OK) return rc;
-    if (e0 != cudaSuccess || e1 != cudaSuccess) {
-        ctx->set_error("trace_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+        ctx->set_error("trace_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
         return PRT_ERR_CUDA;
     }
     return PRT_OK;
