@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PRT_ABI_VERSION 1
+#define PRT_ABI_VERSION 2
 
 typedef struct prt_ctx prt_ctx;
 
@@ -54,7 +54,11 @@ typedef struct {
     float roughness;    /* conductor fuzz, bsdf_taichi.py:49 */
     uint32_t two_sided; /* 1 == reference `sided == 0` (normal flips to face the ray) */
     uint32_t pad;
-} prt_material; /* 32 bytes */
+    float emission[3];  /* radiance of an emitter (Tungsten primitive "emission", e.g. scene.json
+                           [17,12,4]); used by PRT_RENDER_PHYSICAL only -- the reference's own
+                           estimator hard-codes light_color and reads the light's albedo */
+    uint32_t pad2;
+} prt_material; /* 48 bytes */
 
 /* ray record: 2 x float4.  Replaces core/ray.py:5-17 (position, direction,
  * bounds[0], bounds[1]). */
@@ -95,6 +99,13 @@ typedef struct {
 
 /* bounce-0 closest hit runs in PRT_TRACE_EXACT mode: primary-hit ids bit-exact */
 #define PRT_RENDER_EXACT_PRIMARY 1u
+/* physically-based light transport instead of the reference's estimator:
+ * emitters radiate material.emission from their front side, next-event estimation and BSDF
+ * sampling are combined with the power heuristic -- the MIS scheme drafted in the reference's
+ * sample_direct_lighting2 (core/tracing.py:56-90: mis_power_heuristic, compute_area_light_pdf,
+ * compute_brdf_pdf) with the real light area; a path ends on an emitter.  Renders in this mode
+ * agree with media/cornell-box/TungstenRender.exr (tests/test_physical.py). */
+#define PRT_RENDER_PHYSICAL 2u
 
 typedef struct {
     uint32_t n_tris, n_nodes, depth, max_leaf_tris;

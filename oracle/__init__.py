@@ -17,8 +17,8 @@ _SRC = os.path.join(_HERE, "pt_oracle.c")
 
 MATERIAL_DTYPE = np.dtype(
     [("albedo", "<f4", 3), ("type", "<u4"), ("ior", "<f4"), ("roughness", "<f4"),
-     ("two_sided", "<u4"), ("pad", "<u4")])
-assert MATERIAL_DTYPE.itemsize == 32
+     ("two_sided", "<u4"), ("pad", "<u4"), ("emission", "<f4", 3), ("pad2", "<u4")])
+assert MATERIAL_DTYPE.itemsize == 48
 
 
 class Camera(C.Structure):

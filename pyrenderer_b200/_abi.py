@@ -16,11 +16,13 @@ _LIB = None
 
 MATERIAL_DTYPE = np.dtype(
     [("albedo", "<f4", 3), ("type", "<u4"), ("ior", "<f4"), ("roughness", "<f4"),
-     ("two_sided", "<u4"), ("pad", "<u4")])
+     ("two_sided", "<u4"), ("pad", "<u4"), ("emission", "<f4", 3), ("pad2", "<u4")])
+assert MATERIAL_DTYPE.itemsize == 48
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 
 TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE = 1, 2, 4
 RENDER_EXACT_PRIMARY = 1
+RENDER_PHYSICAL = 2
 
 
 class PrtCamera(C.Structure):
@@ -105,7 +107,7 @@ def load():
     for name in EXPORTS:
         if name not in ("prt_destroy", "prt_last_error"):
             getattr(lib, name).restype = C.c_int
-    if lib.prt_abi_version() != 1:
+    if lib.prt_abi_version() != 2:
         raise PrtError("libprt.so ABI version mismatch")
     _LIB = lib
     return lib

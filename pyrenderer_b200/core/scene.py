@@ -83,10 +83,11 @@ class Scene:
         mat_index = {}
         nt = 0
         for pi, prim in enumerate(self.primitives):
-            key = id(prim.bsdf)
+            emission = tuple(float(x) for x in getattr(prim, "emission", (0.0, 0.0, 0.0)))
+            key = (id(prim.bsdf), emission)  # Tungsten puts `emission` on the primitive, not the bsdf
             if key not in mat_index:
                 mat_index[key] = len(mats)
-                mats.append(prim.bsdf.record())
+                mats.append(prim.bsdf.record() + (emission,))
             k = prim.faces.shape[0]
             tris.append(prim.triangles())
             normals.append(prim.normal_vectors)
@@ -96,8 +97,8 @@ class Scene:
                 lights += list(range(nt, nt + k))
             nt += k
         m = np.zeros(len(mats), _abi.MATERIAL_DTYPE)
-        for i, (alb, kind, ior, rough, two) in enumerate(mats):
-            m[i] = (alb, kind, ior, rough, two, 0)
+        for i, (alb, kind, ior, rough, two, emission) in enumerate(mats):
+            m[i] = (alb, kind, ior, rough, two, 0, emission, 0)
         self._arrays = {
             "tris": np.concatenate(tris).astype(np.float32) if tris else np.zeros((0, 3, 3), np.float32),
             "normals": np.concatenate(normals).astype(np.float32) if normals else np.zeros((0, 3), np.float32),

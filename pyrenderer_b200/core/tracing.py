@@ -28,8 +28,12 @@ def new_accum(camera, device=0):
 
 def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_OFF, device=0,
            accum=None, want_prim_ids=False, light_color=LIGHT_COLOR, stream=None,
-           exact_primary=False):
+           exact_primary=False, physical=False):
     """Add samples [spp_begin, spp_begin+spp) to ``accum`` (created if None).
+
+    ``physical`` selects the physically-based estimator (PRT_RENDER_PHYSICAL: scene emission,
+    MIS of light and BSDF sampling -- comparable with Tungsten's render of the same scene)
+    instead of the reference's own estimator (core/tracing.py:116-155).
 
     Returns ``accum`` (torch f32 [h, w, 4]: rgb sums + sample count, row 0 = bottom
     image row), or ``(accum, prim_ids)`` with ``want_prim_ids``.
@@ -45,7 +49,8 @@ def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_O
         ids = torch.full((h, w, spp), -2, dtype=torch.int32, device=accum.device)
     params = ctx.render_params(seed=seed, spp_begin=spp_begin, spp_end=spp_begin + spp,
                                max_depth=max_depth, rr_start=rr_start, light_color=light_color,
-                               tmin=T_MIN, tmax=T_MAX, flags=1 if exact_primary else 0)
+                               tmin=T_MIN, tmax=T_MAX,
+                               flags=(1 if exact_primary else 0) | (2 if physical else 0))
     ctx.render(params, accum, ids, stream)
     return (accum, ids) if want_prim_ids else accum
 

@@ -119,7 +119,7 @@ __global__ void raygen_kernel(CamDev cam, WaveParams P, float4* rays, float4* be
     camera_ray(cam, u, v, ro, rd, P.tmin, P.tmax);
     rays[2 * (size_t)pid] = ro;
     rays[2 * (size_t)pid + 1] = rd;
-    beta[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+    beta[pid] = make_float4(1.f, 1.f, 1.f, -1.f);
     L[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
     queue[pid] = pid;
 }
@@ -134,7 +134,7 @@ __global__ void init_paths_kernel(const float4* __restrict__ user_rays, WavePara
     uint32_t pixel = pid % P.npix;
     rays[2 * (size_t)pid] = user_rays[2 * (size_t)pixel];
     rays[2 * (size_t)pid + 1] = user_rays[2 * (size_t)pixel + 1];
-    beta[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+    beta[pid] = make_float4(1.f, 1.f, 1.f, -1.f);
     L[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
     queue[pid] = pid;
 }
@@ -195,6 +195,18 @@ __device__ __forceinline__ float guard_beta(float albedo, float cz, float pdf) {
     return nb;
 }
 
+__device__ __forceinline__ float tri_area_gid(const SceneDev& sc, uint32_t gid) {
+    const float3 a = xyz(__ldg(sc.verts_gid + 3 * (size_t)gid)), b = xyz(__ldg(sc.verts_gid + 3 * (size_t)gid + 1)),
+                 c = xyz(__ldg(sc.verts_gid + 3 * (size_t)gid + 2));
+    const float3 x = cross(b - a, c - a);
+    return 0.5f * sqrtf(dot(x, x));
+}
+
+// PHYS = PRT_RENDER_PHYSICAL: emitters radiate material.emission, next-event estimation and BSDF
+// sampling are weighted with the power heuristic (the scheme of the reference's draft
+// sample_direct_lighting2, core/tracing.py:56-90), the path ends on an emitter.  beta.w carries
+// the solid-angle pdf of the BSDF sample that produced the current ray (< 0: camera / specular).
+template <bool PHYS>
 __global__ void __launch_bounds__(256)
 shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, float4* rays,
              const float4* __restrict__ hits, float4* beta, float4* L, float4* srays,
@@ -222,9 +234,24 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                 float4 sh = __ldg(sc.shade + gid);
                 float3 n = xyz(sh);
                 const prt_material m = sc.mats[__float_as_uint(sh.w)];
-                float3 b = xyz(beta[pid]);
+                const float4 b4 = beta[pid];
+                float3 b = xyz(b4);
+                float pdf_prev = b4.w;
                 float3 nd = -d;
-                if (m.type == PRT_MAT_EMITTER) {  // core/tracing.py:129-139
+                if (PHYS && m.type == PRT_MAT_EMITTER) {
+                    const float dd = dot(d, d);
+                    const float cl = dot(nd, n) * rsqrtf(dd);
+                    if (cl > 0.0f) {  // one-sided
+                        float w = 1.0f;
+                        if (pdf_prev > 0.0f) {
+                            const float pl = h.x * h.x * dd / (cl * tri_area_gid(sc, (uint32_t)gid) * (float)sc.nl);
+                            w = pdf_prev * pdf_prev / (pdf_prev * pdf_prev + pl * pl);
+                        }
+                        float4 l = L[pid];
+                        L[pid] = make_float4(l.x + b.x * m.emission[0] * w, l.y + b.y * m.emission[1] * w,
+                                             l.z + b.z * m.emission[2] * w, 0.f);
+                    }
+                } else if (m.type == PRT_MAT_EMITTER) {  // core/tracing.py:129-139
                     float d1 = dot(nd, n);
                     if (d1 > 0.0f) {
                         float w = bounce == 0 ? 1.0f : d1;
@@ -249,15 +276,23 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                     float3 wi;
                     bool ok = true, nee = false;
                     float3 alb = make_float3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                    const float3 b_in = b;  // PHYS: the light sample is weighted with the throughput BEFORE this bounce
                     if (m.type == PRT_MAT_LAMBERT) {
                         wi = cosine_sample_hemisphere(n, u24(r1.x), u24(r1.y));
                         float c = dot(n, wi);
-                        float pdf = fabsf(c) * kInvPi;
-                        float cz = fmaxf(c, 0.0f);
-                        b = make_float3(b.x * guard_beta(alb.x, cz, pdf), b.y * guard_beta(alb.y, cz, pdf),
-                                        b.z * guard_beta(alb.z, cz, pdf));
+                        if (PHYS) {
+                            ok = c > 0.0f;
+                            b = b * alb;  // f cos / pdf = albedo
+                            pdf_prev = c * kInvPi;
+                        } else {
+                            float pdf = fabsf(c) * kInvPi;
+                            float cz = fmaxf(c, 0.0f);
+                            b = make_float3(b.x * guard_beta(alb.x, cz, pdf), b.y * guard_beta(alb.y, cz, pdf),
+                                            b.z * guard_beta(alb.z, cz, pdf));
+                        }
                         nee = true;
                     } else {
+                        pdf_prev = -1.0f;
                         float3 ns = (!front && !m.two_sided) ? -n : n;
                         float3 ud = normalize_fast(d);
                         if (m.type == PRT_MAT_MIRROR) {
@@ -278,7 +313,7 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                             b = b * alb;
                         }
                     }
-                    if (ok) {
+                    if (ok || PHYS) {
                         if (nee && sc.nl > 0) {  // core/tracing.py:92-108, shapes.py:62-71
                             uint4 r2 = rng4(P.seed, pixel, s, bounce, 2);
                             uint32_t lt = sc.light_tris[rand_index(r1.z, sc.nl)];
@@ -296,15 +331,24 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                             float dot1 = dot(n, w), dot2 = -dot(xyz(lsh), w);
                             if (dot1 > 0.0f && dot2 > 0.0f) {
                                 const prt_material lm = sc.mats[__float_as_uint(lsh.w)];
-                                float g = dot1 * dot2 / dist2;
                                 want_shadow = true;
                                 sro = make_float4(p.x, p.y, p.z, P.tmin);
                                 srd = make_float4(w.x, w.y, w.z, dist * (1.0f - 1e-4f));
-                                sc4 = make_float4(b.x * lm.albedo[0] * g, b.y * lm.albedo[1] * g,
-                                                  b.z * lm.albedo[2] * g, __uint_as_float(pid));
+                                if (PHYS) {
+                                    const float3 x = cross(v1 - v0, v2 - v0);
+                                    const float pl = dist2 / (dot2 * 0.5f * sqrtf(dot(x, x)) * (float)sc.nl);
+                                    const float pb = dot1 * kInvPi;
+                                    const float g = kInvPi * dot1 * (pl * pl / (pl * pl + pb * pb)) / pl;
+                                    sc4 = make_float4(b_in.x * alb.x * lm.emission[0] * g, b_in.y * alb.y * lm.emission[1] * g,
+                                                      b_in.z * alb.z * lm.emission[2] * g, __uint_as_float(pid));
+                                } else {
+                                    float g = dot1 * dot2 / dist2;
+                                    sc4 = make_float4(b.x * lm.albedo[0] * g, b.y * lm.albedo[1] * g,
+                                                      b.z * lm.albedo[2] * g, __uint_as_float(pid));
+                                }
                             }
                         }
-                        alive = bounce + 1 < max_depth;
+                        alive = ok && bounce + 1 < max_depth;
                         if (bounce >= P.rr_start) {
                             float q = fmaxf(b.x, fmaxf(b.y, b.z));
                             if (q < 1.0f) {
@@ -313,7 +357,7 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                             }
                         }
                         if (alive) {
-                            beta[pid] = make_float4(b.x, b.y, b.z, 0.f);
+                            beta[pid] = make_float4(b.x, b.y, b.z, pdf_prev);
                             rays[2 * (size_t)pid] = make_float4(p.x, p.y, p.z, P.tmin);
                             rays[2 * (size_t)pid + 1] = make_float4(wi.x, wi.y, wi.z, P.tmax);
                         }
@@ -410,7 +454,7 @@ static int wave_alloc(prt_ctx* ctx, uint64_t cap) {
     w->cap = cap;
     int bt = 0, bs = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, closest_kernel, kTraceThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, shade_kernel, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, shade_kernel<false>, 256, 0);
     w->grid_trace = ctx->num_sms * (bt > 0 ? bt : 4);
     w->grid_shade = ctx->num_sms * (bs > 0 ? bs : 4);
     return PRT_OK;
@@ -457,8 +501,12 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
             } else {
                 closest_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt);
             }
-            shade_kernel<<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
-                                                            w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
+            if (p->flags & PRT_RENDER_PHYSICAL)
+                shade_kernel<true><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
+                                                                      w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
+            else
+                shade_kernel<false><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
+                                                                       w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
             shadow_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->srays, w->scontrib, w->L, w->cnt);
             advance_kernel<<<1, 1, 0, stream>>>(w->cnt, ctx->counters);
         }

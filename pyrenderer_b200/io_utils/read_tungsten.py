@@ -61,6 +61,10 @@ def process_primitives(data, base_dir="."):
         else:
             print(f"[WARNING] {kind} not implemented")
             continue
+        # radiance of an emitter (scene.json:234-238; ignored by the reference, used by the
+        # physically-based mode)
+        e = np.asarray(info.get("emission", 0.0), np.float64).reshape(-1)
+        prim.emission = np.full(3, e[0]) if e.size == 1 else e[:3].copy()
         a_scene.add_primitive(prim)
     return a_scene, a_camera
 

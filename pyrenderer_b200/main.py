@@ -36,14 +36,14 @@ def write_png(path, rgb8):
 
 
 def main(scene_file=DEFAULT_SCENE, samples=8, max_depth=5, width=None, height=None, seed=1,
-         out="test.png", tonemap=None, device=0):
+         out="test.png", tonemap=None, device=0, physical=False):
     a_scene, a_camera = read_file(scene_file)
     if width and height:
         a_camera.resolution = [width, height]
     import torch
     t0 = time.time()
     accum = tracing.render(a_scene, a_camera, spp=samples, max_depth=max_depth, seed=seed,
-                           device=device)
+                           device=device, physical=physical)
     torch.cuda.synchronize()
     dt = time.time() - t0
     image = tracing.to_uint8(tracing.to_image(accum, tonemap))
@@ -92,8 +92,10 @@ if __name__ == "__main__":
     ap.add_argument("--tonemap", default=None, choices=[None, "sqrt", "reinhard"])
     ap.add_argument("--progressive", type=int, default=0, metavar="N",
                     help="main_taichi.py-style loop: N iterations of 1 spp into one buffer")
+    ap.add_argument("--physical", action="store_true",
+                    help="physically-based estimator (scene emission + MIS) instead of the reference's")
     a = ap.parse_args()
     if a.progressive:
         main_progressive(a.scene, a.progressive, a.max_depth, a.seed, a.out)
         raise SystemExit(0)
-    main(a.scene, a.samples, a.max_depth, a.width, a.height, a.seed, a.out, a.tonemap)
+    main(a.scene, a.samples, a.max_depth, a.width, a.height, a.seed, a.out, a.tonemap, physical=a.physical)

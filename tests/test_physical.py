@@ -1,0 +1,136 @@
+"""Physically-based mode (PRT_RENDER_PHYSICAL): scene emission + MIS.
+
+External anchor: media/cornell-box/TungstenRender.exr, the one image in the reference repository
+that was not produced by pyrenderer -- Tungsten's render of the same scene.json.  The fixture
+tests/golden/tungsten_cornell_128.npz holds its 8x8-pixel block means
+(tests/golden/make_tungsten_fixture.py).  A correct unbiased estimator of the same light
+transport converges to the same block means; Tungsten's tent reconstruction filter only moves
+energy between neighbouring pixels, so blocks that contain the light's edge are left out of the
+per-block comparison (they stay in the whole-image mean).
+
+  * oracle (CPU, f64) vs Tungsten: whole-image mean within 0.5 %, block rel. RMSE small
+  * GPU vs oracle at equal seed/spp: same paths, relative RMSE < 1e-3 (north_star tolerance)
+  * GPU vs Tungsten at 4096 spp: whole-image mean within 0.3 %, per-region means within 1.5 %
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT
+
+FIXTURE = os.path.join(ROOT, "tests", "golden", "tungsten_cornell_128.npz")
+PHYSICAL = 2
+
+
+def tungsten():
+    return np.load(FIXTURE)["mean"].astype(np.float64)  # [128,128,3], row 0 = top
+
+
+def blocks(img, b):
+    h, w, _ = img.shape
+    return img.reshape(h // b, b, w // b, b, 3).mean(axis=(1, 3))
+
+
+def compare(img_top_down, ref, label):
+    """img_top_down, ref: [128,128,3].  Returns (mean ratio, rel RMSE over 8x8 super-blocks that
+    do not touch the light)."""
+    ratio = img_top_down.mean() / ref.mean()
+    A, B = blocks(img_top_down, 8), blocks(ref, 8)  # 16 x 16 super-blocks of 64x64 pixels
+    keep = np.ones(A.shape[:2], bool)
+    keep[0:2, 5:11] = False  # light: rows 73-94, cols 406-613 of 1024 (+ filter rim)
+    rmse = float(np.sqrt(np.mean((A[keep] - B[keep]) ** 2)) / np.mean(B[keep]))
+    print(f"[{label}] mean ratio {ratio:.4f}  super-block rel RMSE (light excluded) {rmse:.4f}")
+    return ratio, rmse
+
+
+def scene_arrays(cornell, w, h):
+    scene, cam = cornell
+    a = scene.arrays()
+    iview, sw, sh, focal, _, _ = cam.device_record()
+    return a, (iview, sh * (w / h), sh, focal, w, h)
+
+
+def test_loader_reads_emission(cornell):
+    a = cornell[0].arrays()
+    m = a["materials"]
+    light = m[a["tri_material"][a["light_tris"][0]]]
+    assert light["type"] == 1 and np.allclose(light["emission"], [17, 12, 4])
+    assert all(np.all(x["emission"] == 0) for x in m if x["type"] != 1)
+
+
+def test_oracle_physical_matches_tungsten(cornell):
+    a, camrec = scene_arrays(cornell, 128, 128)
+    ocam = oracle.make_camera(*camrec)
+    P = oracle.make_params(seed=5, spp_begin=0, spp_end=160, max_depth=16, tmax=3e38, flags=PHYSICAL)
+    acc = oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"], ocam, P)[0]
+    img = (acc[..., :3] / acc[..., 3:4])[::-1]  # accumulation buffers are bottom-up
+    ratio, rmse = compare(img, tungsten(), "oracle 160 spp")
+    assert abs(ratio - 1.0) < 5e-3
+    assert rmse < 0.02
+
+
+def test_oracle_physical_known_answers(cornell):
+    """Pixels whose samples all hit the light return exactly its emission; with depth 1 every other
+    pixel holds one direct-lighting estimate: finite, non-negative, and zero on the ceiling (which
+    faces away from the light's emitting side)."""
+    a, camrec = scene_arrays(cornell, 64, 64)
+    ocam = oracle.make_camera(*camrec)
+    P = oracle.make_params(seed=1, spp_begin=0, spp_end=4, max_depth=1, tmax=3e38, flags=PHYSICAL)
+    acc, ids, _ = oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"], ocam, P,
+                                want_ids=True)
+    img = acc[..., :3] / acc[..., 3:4]
+    lit = np.isin(ids, a["light_tris"]).all(axis=2)
+    assert lit.sum() > 5 and np.allclose(img[lit], [17, 12, 4])
+    rest = img[~np.isin(ids, a["light_tris"]).any(axis=2)]
+    assert np.isfinite(rest).all() and np.all(rest >= 0) and rest.max() < 17
+    ceiling = np.isin(ids, [2, 3]).all(axis=2)  # global ids 2-3 = Ceiling
+    assert ceiling.sum() > 20 and np.all(img[ceiling] == 0)
+
+
+@pytest.mark.gpu
+def test_gpu_physical_equals_oracle_at_equal_seed(gpu_ctx, cornell):
+    import torch
+    W = H = 96
+    a, camrec = scene_arrays(cornell, W, H)
+    gpu_ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])
+    gpu_ctx.build_bvh()
+    gpu_ctx.set_camera(*camrec)
+    kw = dict(seed=9, spp_begin=2, spp_end=34, max_depth=8, tmax=3e38, flags=PHYSICAL)
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    gpu_ctx.render(gpu_ctx.render_params(**kw), acc)
+    torch.cuda.synchronize()
+    g = acc.cpu().numpy().astype(np.float64)
+    o = oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"],
+                      oracle.make_camera(*camrec), oracle.make_params(**kw))[0]
+    assert np.array_equal(g[..., 3], o[..., 3])
+    err = float(np.sqrt(np.mean((g[..., :3] - o[..., :3]) ** 2)) / np.mean(o[..., :3]))
+    print(f"[physical] GPU vs oracle, equal seed, 32 spp: rel RMSE {err:.2e}")
+    assert err < 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_physical_matches_tungsten(gpu_ctx, cornell):
+    import torch
+    W = H = 128
+    a, camrec = scene_arrays(cornell, W, H)
+    gpu_ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])
+    gpu_ctx.build_bvh()
+    gpu_ctx.set_camera(*camrec)
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    for s0 in range(0, 4096, 512):
+        gpu_ctx.render(gpu_ctx.render_params(seed=11, spp_begin=s0, spp_end=s0 + 512, max_depth=24, tmax=3e38,
+                                             flags=PHYSICAL), acc)
+    torch.cuda.synchronize()
+    g = acc.cpu().numpy().astype(np.float64)
+    img = (g[..., :3] / g[..., 3:4])[::-1]
+    ref = tungsten()
+    ratio, rmse = compare(img, ref, "GPU 4096 spp")
+    assert abs(ratio - 1.0) < 3e-3
+    assert rmse < 0.01
+    for name, sl in (("floor", (slice(100, 128), slice(0, 128))), ("left wall", (slice(20, 110), slice(0, 20))),
+                     ("right wall", (slice(20, 110), slice(108, 128))), ("back wall", (slice(30, 60), slice(40, 90)))):
+        r = img[sl].mean(axis=(0, 1)) / ref[sl].mean(axis=(0, 1))
+        print(f"[GPU 4096 spp] {name}: rgb ratio {np.round(r, 4)}")
+        assert np.all(np.abs(r - 1.0) < 0.015), name
