@@ -213,11 +213,17 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
              float4* scontrib, const uint32_t* __restrict__ queue_in, uint32_t* queue_out,
              unsigned int* cnt, int32_t* prim_ids) {
     const unsigned int n = cnt[0];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int stride = gridDim.x * blockDim.x;
-    // round the loop bound up to a whole warp so ballots see all lanes
-    for (unsigned int k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < n; k0 += stride) {
-        unsigned int k = k0 + lane;
+    // queue compaction is aggregated per BLOCK (ballot -> per-warp counts in shared memory -> one
+    // atomicAdd per queue per block iteration): with one atomic per warp the two queue tails took
+    // 0.5 M same-address atomics per launch and 56 % of this kernel's stall samples were lanes
+    // waiting for them (profiles/r1_shade_kernel_ncu.txt).  Double-buffered by iteration parity.
+    __shared__ unsigned int s_cnt[2][2][8], s_base[2][2];
+    unsigned int parity = 0;
+    // block-uniform trip count, so the barriers below are reached by every thread
+    for (unsigned int kb = blockIdx.x * blockDim.x; kb < n; kb += stride, parity ^= 1u) {
+        unsigned int k = kb + threadIdx.x;
         bool alive = false, want_shadow = false;
         uint32_t pid = 0;
         float4 sro, srd, sc4;
@@ -365,16 +371,20 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                 }
             }
         }
-        // warp-aggregated compaction: ballot + prefix popcount, one atomic per warp per queue
+        // block-aggregated compaction: ballot + prefix popcount, one atomic per block per queue
         unsigned int am = __ballot_sync(0xffffffffu, alive);
         unsigned int sm = __ballot_sync(0xffffffffu, want_shadow);
-        unsigned int abase = 0, sbase = 0;
-        if (lane == 0) {
-            if (am) abase = atomicAdd(cnt + 1, (unsigned int)__popc(am));
-            if (sm) sbase = atomicAdd(cnt + 2, (unsigned int)__popc(sm));
+        if (lane == 0) { s_cnt[parity][0][warp] = __popc(am); s_cnt[parity][1][warp] = __popc(sm); }
+        __syncthreads();
+        if (threadIdx.x < 2) {  // thread q reserves queue q
+            unsigned int tot = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) tot += s_cnt[parity][threadIdx.x][w8];
+            s_base[parity][threadIdx.x] = tot ? atomicAdd(cnt + 1 + threadIdx.x, tot) : 0u;
         }
-        abase = __shfl_sync(0xffffffffu, abase, 0);
-        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        __syncthreads();
+        unsigned int abase = s_base[parity][0], sbase = s_base[parity][1];
+        for (int w8 = 0; w8 < warp; ++w8) { abase += s_cnt[parity][0][w8]; sbase += s_cnt[parity][1][w8]; }
         unsigned int lt_mask = (1u << lane) - 1u;
         if (alive) queue_out[abase + __popc(am & lt_mask)] = pid;
         if (want_shadow) {
