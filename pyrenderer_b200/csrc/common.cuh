@@ -40,7 +40,7 @@ struct SceneDev {
     const uint32_t* light_tris;  // global ids
     const float4* verts_gid;     // [nt*3] by global id (light sampling)
     uint32_t nt, n_nodes, nl, nm;
-    int refill_idle, leaf_batch;  // persist.cuh scheduling knobs
+    int refill_idle, leaf_batch, fetch_chunk;  // persist.cuh scheduling knobs
 };
 
 struct Counters {

@@ -62,16 +62,35 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
         return;
     }
 
+    // Ray indices are reserved per warp in chunks of sc.fetch_chunk with ONE atomic per chunk, and
+    // the next chunk is requested when the current one is entered, i.e. long before it is needed:
+    // idle lanes never wait for an atomic round trip (one atomic per refill made the fetch counter
+    // a same-address hot spot: 1-2 M atomics per launch on short traversals).
+    const unsigned chunk = (unsigned)sc.fetch_chunk;
+    unsigned r_next = 0, r_end = 0, p_base = 0;  // warp-uniform: current reservation; p_base (lane 0): prefetched chunk
+    if (lane == 0) {
+        r_next = atomicAdd(fetch, chunk);
+        p_base = atomicAdd(fetch, chunk);
+    }
+    r_next = __shfl_sync(FULL, r_next, 0);
+    r_end = r_next + chunk;
+
     while (true) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(FULL, !has_ray);
         if (!exhausted && (__popc(idle) >= sc.refill_idle)) {
-            unsigned base = 0;
-            const int leader = __ffs(idle) - 1, nidle = __popc(idle);
-            if (lane == leader) base = atomicAdd(fetch, (unsigned)nidle);
-            base = __shfl_sync(FULL, base, leader);
+            const unsigned nidle = __popc(idle), pre = __popc(idle & lt), rem = r_end - r_next;
+            unsigned k = r_next + pre;
+            if (nidle > rem) {  // warp-uniform: continue in the prefetched chunk, request the one after it
+                const unsigned pb = __shfl_sync(FULL, p_base, 0);
+                if (pre >= rem) k = pb + (pre - rem);
+                r_next = pb + (nidle - rem);
+                r_end = pb + chunk;
+                if (lane == 0) p_base = atomicAdd(fetch, chunk);
+            } else {
+                r_next += nidle;
+            }
             if (!has_ray) {
-                const unsigned k = base + __popc(idle & lt);
                 if (k < n) {
                     float4 ro, rd;
                     io.load(k, ro, rd, tag);
@@ -86,7 +105,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     if (COUNT) ++c_rays;
                 }
             }
-            if (base + (unsigned)nidle >= n) exhausted = true;
+            if (r_next >= n) exhausted = true;  // chunk bases only grow: nothing at or after r_next is left
         }
         if (exhausted && __ballot_sync(FULL, has_ray) == 0) break;  // (idle mask may be stale after a refill)
 

@@ -110,6 +110,7 @@ int prt_create(int device, prt_ctx** out) {
     c->device = device;
     if (const char* v = getenv("PRT_REFILL_IDLE")) c->refill_idle = atoi(v) > 0 ? atoi(v) : c->refill_idle;
     if (const char* v = getenv("PRT_LEAF_BATCH")) c->leaf_batch = atoi(v) > 0 ? atoi(v) : c->leaf_batch;
+    if (const char* v = getenv("PRT_FETCH_CHUNK")) c->fetch_chunk = atoi(v) > 0 ? atoi(v) : c->fetch_chunk;
     e = cudaSetDevice(device);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
