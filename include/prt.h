@@ -138,6 +138,8 @@ typedef struct {
     float cost_node;        /* SAH traversal cost, default 1.0 */
     float cost_tri;         /* SAH intersection cost, default 2.0 */
     uint32_t rotations;     /* number of bottom-up SAH rotation passes during refit (0 = none, default 1) */
+    uint32_t treelets;      /* 1 (default): every maximal subtree of <= 64 triangles of the Morton
+                               hierarchy is rebuilt with binned SAH before refit; 0 = plain LBVH */
 } prt_bvh_options;
 
 int prt_abi_version(void);

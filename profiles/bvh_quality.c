@@ -51,8 +51,12 @@ static void morton_sort(void) {
     }
     qsort(mk, N, sizeof(uint64_t), cmp64);
 }
+static int sah_rec(int a, int b);
+static int* idx;
+static int HYB = 0; /* hybrid: Morton ranges of <= HYB triangles are rebuilt by SAH */
 static int lbvh_rec(int a, int b) { /* [a,b] inclusive */
     if (a == b) return new_leaf((int)(mk[a] & 0xffffffffu));
+    if (b - a + 1 <= HYB) { for (int i = a; i <= b; ++i) idx[i] = (int)(mk[i] & 0xffffffffu); return sah_rec(a, b + 1); }
     uint32_t ka = mk[a] >> 32, kb = mk[b] >> 32; int split;
     if (ka == kb) split = (a + b) / 2;
     else { int p = __builtin_clz(ka ^ kb); int lo = a, hi = b; /* last index whose key shares > p bits with ka */
@@ -63,7 +67,6 @@ static int lbvh_rec(int a, int b) { /* [a,b] inclusive */
 }
 
 /* ---------------- binned SAH */
-static int* idx;
 static int sah_rec(int a, int b) { /* [a,b) */
     if (b - a == 1) return new_leaf(idx[a]);
     Box cb = empty_box();
@@ -206,9 +209,12 @@ int main(int argc, char** argv) {
     nodes = malloc(sizeof(BNode) * 2 * N); wn = malloc(sizeof(WNode) * N);
     morton_sort();
     const char* which = argc > 4 ? argv[4] : "lbvh,sah,ploc8,ploc16";
+    idx = malloc(sizeof(int) * N);
+    if (strstr(which, "hyb")) for (HYB = 4; HYB <= 4096; HYB *= 4) { char nm[32]; sprintf(nm, "hybrid%d", HYB); n_nodes = 0; int root = lbvh_rec(0, N - 1); collapse(root); trace(rays, nr, nm, sah_binary(root)); }
+    HYB = 0;
     if (strstr(which, "lbvh")) { n_nodes = 0; int root = lbvh_rec(0, N - 1); collapse(root); trace(rays, nr, "lbvh", sah_binary(root));
         for (CT = 0.5f; CT <= 4.0f; CT *= 2.f) { char nm[32]; sprintf(nm, "lbvh-dp%.1f", CT); collapse_dp(root); trace(rays, nr, nm, sah_binary(root)); } }
-    if (strstr(which, "sah")) { n_nodes = 0; idx = malloc(sizeof(int) * N); for (int i = 0; i < N; ++i) idx[i] = i; int root = sah_rec(0, N); collapse(root); trace(rays, nr, "sah", sah_binary(root));
+    if (strstr(which, "sah")) { n_nodes = 0; for (int i = 0; i < N; ++i) idx[i] = i; int root = sah_rec(0, N); collapse(root); trace(rays, nr, "sah", sah_binary(root));
         CT = 1.0f; collapse_dp(root); trace(rays, nr, "sah-dp1.0", sah_binary(root)); }
     for (int R = 4; R <= 64; R *= 2) { char nm[16]; sprintf(nm, "ploc%d", R); if (!strstr(which, nm)) continue; n_nodes = 0; int root = ploc_build(R); collapse(root); trace(rays, nr, nm, sah_binary(root)); }
     return 0;

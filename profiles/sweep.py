@@ -50,6 +50,17 @@ def main():
             st = ctx.build_bvh(max_leaf_tris=1, rotations=rot)
             m, nn, nt = measure(ctx, r, hits)
             print(f"rotation passes {rot}: {m:8.1f} Mrays/s  N_node {nn:6.2f} N_tri {nt:5.2f} sah {st['sah_cost']:.1f} build {st['ms_total']:.2f} ms (refit {st['ms_refit']:.2f})", flush=True)
+    elif mode == "treelet":
+        ctx = _abi.Context(0)
+        for tl in (0, 1):
+            for rot in (0, 1):
+                ctx.set_triangles_dev(tris, 1_000_000)
+                st = ctx.build_bvh(treelets=tl, rotations=rot)
+                ms = []
+                for _ in range(4):
+                    ms.append(ctx.build_bvh(treelets=tl, rotations=rot)["ms_total"])
+                m, nn, nt = measure(ctx, r, hits)
+                print(f"treelets {tl} rotations {rot}: {m:8.1f} Mrays/s  N_node {nn:6.2f} N_tri {nt:5.2f} nodes {st['n_nodes']} depth {st['depth']} sah {st['sah_cost']:.1f} build {np.median(ms):.2f} ms (hierarchy+treelets {st['ms_hierarchy']:.2f})", flush=True)
     elif mode == "util":
         ctx = _abi.Context(0)
         ctx.set_triangles_dev(tris, 1_000_000)

@@ -9,8 +9,9 @@ VDIR = os.path.join(ROOT, "pyrenderer_b200", "variants")
 # -6 %, PRMT+FADD byte->float instead of I2F.U8 -8 %, L1 prefetch of the far child 0 %, smem stack
 # depth 8/12/16 no effect -- none of them is in the tree any more; add -D switches here to try new ones.
 VARIANTS = {
-    "base": ("-DPRT_PREFETCH_TRI=0",),
-    "pftri": ("-DPRT_PREFETCH_TRI=1",),
+    "t64": ("-DPRT_TREELET=64",),
+    "t128": ("-DPRT_TREELET=128",),
+    "t192": ("-DPRT_TREELET=192",),
 }
 if sys.argv[1] == "build":
     from pyrenderer_b200 import build

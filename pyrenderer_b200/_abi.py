@@ -46,7 +46,7 @@ class PrtBvhStats(C.Structure):
 
 class PrtBvhOptions(C.Structure):
     _fields_ = [("max_leaf_tris", C.c_uint32), ("cost_node", C.c_float), ("cost_tri", C.c_float),
-                ("rotations", C.c_uint32)]
+                ("rotations", C.c_uint32), ("treelets", C.c_uint32)]
 
 
 class PrtCounters(C.Structure):
@@ -178,8 +178,8 @@ class Context:
         self._check(self.lib.prt_scene_set_triangles_dev(self.h, _dev_ptr(verts_dev), int(nt),
                                                          _stream_ptr(stream)))
 
-    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=2.0, rotations=1):
-        opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations))
+    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=2.0, rotations=1, treelets=1):
+        opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations), int(treelets))
         st = PrtBvhStats()
         self._check(self.lib.prt_bvh_build(self.h, C.byref(opts), C.byref(st)))
         return {k: getattr(st, k) for k, _ in PrtBvhStats._fields_}
