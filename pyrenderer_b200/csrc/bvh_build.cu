@@ -172,7 +172,6 @@ __global__ void hierarchy_kernel(const uint32_t* __restrict__ keys, int n, int* 
 #define PRT_TREELET 128
 #endif
 constexpr int kTreelet = PRT_TREELET;  // <= 255 (8-bit permutation)
-constexpr int kTreeletBins = 16;
 constexpr int kTreeletWarps = 4;  // warps per block
 
 __global__ void treelet_roots_kernel(const int2* __restrict__ range, const int* __restrict__ parent, int n,
@@ -200,6 +199,71 @@ struct TreeletShared {
 __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
     const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
     return 2.0f * (x * y + y * z + z * x);
+}
+
+// Best binned-SAH plane of order[b, e) with NB bins per axis.  Lane (axis, bin) scans the range and
+// keeps its bin's box in registers; prefix / suffix unions over the NB bins of an axis are shuffle
+// scans inside an NB-lane group; candidate plane j = "bins <= j go left".  NB = 16: two rounds
+// (axes x,y then z); NB = 8: the 24 (axis, bin) pairs fit one round.  Returns cost (inf: none).
+template <int NB>
+__device__ __forceinline__ float treelet_best_split(const TreeletShared& S, int b, int e, const float cmin[3],
+                                                    const float scale[3], int lane, int& best_slot) {
+    const unsigned FULL = 0xffffffffu;
+    const float inf = __int_as_float(0x7f800000);
+    constexpr int kAxesPerRound = 32 / NB;             // 2 or 4 (4th group idle)
+    constexpr int kRounds = NB == 16 ? 2 : 1;
+    float best = inf;
+    best_slot = -1;
+#pragma unroll
+    for (int round = 0; round < kRounds; ++round) {
+        const int a = lane / NB + kAxesPerRound * round, bin = lane % NB;
+        const float cm_a = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);  // selects: no dynamic indexing
+        const float sc_a = a == 0 ? scale[0] : (a == 1 ? scale[1] : (a == 2 ? scale[2] : 0.0f));
+        float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+        int cnt = 0;
+        if (sc_a > 0.0f) {
+            for (int k = b; k < e; ++k) {
+                const int q = S.order[k];
+                int j = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
+                j = j > NB - 1 ? NB - 1 : j;
+                if (j == bin) {
+                    l0 = fminf(l0, S.lo[q][0]); l1 = fminf(l1, S.lo[q][1]); l2 = fminf(l2, S.lo[q][2]);
+                    h0 = fmaxf(h0, S.hi[q][0]); h1 = fmaxf(h1, S.hi[q][1]); h2 = fmaxf(h2, S.hi[q][2]);
+                    ++cnt;
+                }
+            }
+        }
+        // inclusive prefix (bins 0..bin) and suffix (bins bin..NB-1) within the NB-lane group
+        float p0 = l0, p1 = l1, p2 = l2, q0 = h0, q1 = h1, q2 = h2;
+        float s0 = l0, s1 = l1, s2 = l2, t0 = h0, t1 = h1, t2 = h2;
+        int pc = cnt, sc2 = cnt;
+#pragma unroll
+        for (int o = 1; o < NB; o <<= 1) {
+            const float a0 = __shfl_up_sync(FULL, p0, o, NB), a1 = __shfl_up_sync(FULL, p1, o, NB), a2 = __shfl_up_sync(FULL, p2, o, NB);
+            const float b0 = __shfl_up_sync(FULL, q0, o, NB), b1 = __shfl_up_sync(FULL, q1, o, NB), b2 = __shfl_up_sync(FULL, q2, o, NB);
+            const int ac = __shfl_up_sync(FULL, pc, o, NB);
+            if (bin >= o) { p0 = fminf(p0, a0); p1 = fminf(p1, a1); p2 = fminf(p2, a2); q0 = fmaxf(q0, b0); q1 = fmaxf(q1, b1); q2 = fmaxf(q2, b2); pc += ac; }
+            const float c0 = __shfl_down_sync(FULL, s0, o, NB), c1 = __shfl_down_sync(FULL, s1, o, NB), c2 = __shfl_down_sync(FULL, s2, o, NB);
+            const float d0 = __shfl_down_sync(FULL, t0, o, NB), d1 = __shfl_down_sync(FULL, t1, o, NB), d2 = __shfl_down_sync(FULL, t2, o, NB);
+            const int dc = __shfl_down_sync(FULL, sc2, o, NB);
+            if (bin + o < NB) { s0 = fminf(s0, c0); s1 = fminf(s1, c1); s2 = fminf(s2, c2); t0 = fmaxf(t0, d0); t1 = fmaxf(t1, d1); t2 = fmaxf(t2, d2); sc2 += dc; }
+        }
+        // right side of candidate `bin` = suffix of bin + 1
+        const float r0 = __shfl_down_sync(FULL, s0, 1, NB), r1 = __shfl_down_sync(FULL, s1, 1, NB), r2 = __shfl_down_sync(FULL, s2, 1, NB);
+        const float u0 = __shfl_down_sync(FULL, t0, 1, NB), u1 = __shfl_down_sync(FULL, t1, 1, NB), u2 = __shfl_down_sync(FULL, t2, 1, NB);
+        const int rc = __shfl_down_sync(FULL, sc2, 1, NB);
+        if (a < 3 && bin < NB - 1 && pc > 0 && rc > 0) {
+            const float pl[3] = {p0, p1, p2}, ph[3] = {q0, q1, q2}, rl[3] = {r0, r1, r2}, rh[3] = {u0, u1, u2};
+            const float cost = area3(pl, ph) * (float)pc + area3(rl, rh) * (float)rc;
+            if (cost < best) { best = cost; best_slot = a * NB + bin; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o);
+        const int os = __shfl_xor_sync(FULL, best_slot, o);
+        if (ob < best || (ob == best && os >= 0 && (best_slot < 0 || os < best_slot))) { best = ob; best_slot = os; }
+    }
+    return best;
 }
 
 __global__ void __launch_bounds__(32 * kTreeletWarps)
@@ -270,64 +334,16 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                         cmin[a] = fminf(cmin[a], __shfl_xor_sync(FULL, cmin[a], o));
                         cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(FULL, cmax[a], o));
                     }
+                // 16 bins for the large ranges near the treelet root, 8 (one round) below
+                const int nb = c > 32 ? 16 : 8;
                 float scale[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) scale[a] = cmax[a] > cmin[a] ? (float)kTreeletBins / (cmax[a] - cmin[a]) : 0.0f;
-                // Lane (axis, bin) = (lane / 16 + 2 * round, lane % 16) scans the range and keeps its bin's
-                // box in registers; prefix / suffix unions over the 16 bins of an axis are two
-                // shuffle scans inside the half-warp; candidate plane j = "bins <= j go left".
-                float best = inf;
-                int best_slot = -1;
-                for (int round = 0; round < 2; ++round) {
-                    const int a = (lane >> 4) + 2 * round, bin = lane & 15;
-                    float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
-                    int cnt = 0;
-                    const float cm_a = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);  // selects: no dynamic indexing
-                    const float sc_a = a == 0 ? scale[0] : (a == 1 ? scale[1] : (a == 2 ? scale[2] : 0.0f));
-                    if (sc_a > 0.0f) {
-                        for (int k = b; k < e; ++k) {
-                            const int q = S.order[k];
-                            int j = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
-                            j = j > kTreeletBins - 1 ? kTreeletBins - 1 : j;
-                            if (j == bin) {
-                                l0 = fminf(l0, S.lo[q][0]); l1 = fminf(l1, S.lo[q][1]); l2 = fminf(l2, S.lo[q][2]);
-                                h0 = fmaxf(h0, S.hi[q][0]); h1 = fmaxf(h1, S.hi[q][1]); h2 = fmaxf(h2, S.hi[q][2]);
-                                ++cnt;
-                            }
-                        }
-                    }
-                    // inclusive prefix (bins 0..bin) and suffix (bins bin..15) within the half-warp
-                    float p0 = l0, p1 = l1, p2 = l2, q0 = h0, q1 = h1, q2 = h2;
-                    float s0 = l0, s1 = l1, s2 = l2, t0 = h0, t1 = h1, t2 = h2;
-                    int pc = cnt, sc2 = cnt;
-#pragma unroll
-                    for (int o = 1; o < 16; o <<= 1) {
-                        const float a0 = __shfl_up_sync(FULL, p0, o, 16), a1 = __shfl_up_sync(FULL, p1, o, 16), a2 = __shfl_up_sync(FULL, p2, o, 16);
-                        const float b0 = __shfl_up_sync(FULL, q0, o, 16), b1 = __shfl_up_sync(FULL, q1, o, 16), b2 = __shfl_up_sync(FULL, q2, o, 16);
-                        const int ac = __shfl_up_sync(FULL, pc, o, 16);
-                        if (bin >= o) { p0 = fminf(p0, a0); p1 = fminf(p1, a1); p2 = fminf(p2, a2); q0 = fmaxf(q0, b0); q1 = fmaxf(q1, b1); q2 = fmaxf(q2, b2); pc += ac; }
-                        const float c0 = __shfl_down_sync(FULL, s0, o, 16), c1 = __shfl_down_sync(FULL, s1, o, 16), c2 = __shfl_down_sync(FULL, s2, o, 16);
-                        const float d0 = __shfl_down_sync(FULL, t0, o, 16), d1 = __shfl_down_sync(FULL, t1, o, 16), d2 = __shfl_down_sync(FULL, t2, o, 16);
-                        const int dc = __shfl_down_sync(FULL, sc2, o, 16);
-                        if (bin + o < 16) { s0 = fminf(s0, c0); s1 = fminf(s1, c1); s2 = fminf(s2, c2); t0 = fmaxf(t0, d0); t1 = fmaxf(t1, d1); t2 = fmaxf(t2, d2); sc2 += dc; }
-                    }
-                    // right side of candidate `bin` = suffix of bin + 1
-                    const float r0 = __shfl_down_sync(FULL, s0, 1, 16), r1 = __shfl_down_sync(FULL, s1, 1, 16), r2 = __shfl_down_sync(FULL, s2, 1, 16);
-                    const float u0 = __shfl_down_sync(FULL, t0, 1, 16), u1 = __shfl_down_sync(FULL, t1, 1, 16), u2 = __shfl_down_sync(FULL, t2, 1, 16);
-                    const int rc = __shfl_down_sync(FULL, sc2, 1, 16);
-                    if (a < 3 && bin < kTreeletBins - 1 && pc > 0 && rc > 0) {
-                        const float pl[3] = {p0, p1, p2}, ph[3] = {q0, q1, q2}, rl[3] = {r0, r1, r2}, rh[3] = {u0, u1, u2};
-                        const float cost = area3(pl, ph) * (float)pc + area3(rl, rh) * (float)rc;
-                        if (cost < best) { best = cost; best_slot = a * kTreeletBins + bin; }
-                    }
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(FULL, best, o);
-                    const int os = __shfl_xor_sync(FULL, best_slot, o);
-                    if (ob < best || (ob == best && os >= 0 && (best_slot < 0 || os < best_slot))) { best = ob; best_slot = os; }
-                }
+                for (int a = 0; a < 3; ++a) scale[a] = cmax[a] > cmin[a] ? (float)nb / (cmax[a] - cmin[a]) : 0.0f;
+                int best_slot;
+                if (nb == 16) treelet_best_split<16>(S, b, e, cmin, scale, lane, best_slot);
+                else treelet_best_split<8>(S, b, e, cmin, scale, lane, best_slot);
                 if (best_slot >= 0) {
-                    const int a = best_slot / kTreeletBins, j = best_slot % kTreeletBins;
+                    const int a = best_slot / nb, j = best_slot % nb;
                     const float cm_a = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);
                     const float sc_a = a == 0 ? scale[0] : (a == 1 ? scale[1] : scale[2]);
                     // stable partition of order[b, e) by bin <= j
@@ -339,7 +355,7 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                         if (k < e) {
                             q = S.order[k];
                             int bj = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
-                            bj = bj > kTreeletBins - 1 ? kTreeletBins - 1 : bj;
+                            bj = bj > nb - 1 ? nb - 1 : bj;
                             go_left = bj <= j;
                         }
                         const unsigned lm = __ballot_sync(FULL, go_left);
@@ -354,7 +370,7 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                         if (k < e) {
                             q = S.order[k];
                             int bj = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
-                            bj = bj > kTreeletBins - 1 ? kTreeletBins - 1 : bj;
+                            bj = bj > nb - 1 ? nb - 1 : bj;
                             go_right = bj > j;
                         }
                         const unsigned rm = __ballot_sync(FULL, go_right);
