@@ -39,6 +39,9 @@ N_BATCHES = 4
 HBM_FALLBACK_GBS = 6650.0
 
 
+NCU_DRAM_BYTES_PER_LAUNCH = 3.600135e9 + 0.378812e9  # gpurun r41 capture
+
+
 def soup(n, seed=7):
     rng = np.random.default_rng(seed)
     h = 0.75 * n ** (-1.0 / 3.0)
@@ -365,8 +368,16 @@ def main():
             "gpu_launches": args.steps * 1,  # timed region of `value`: one trace_persistent_kernel per step (render leg: see render.gpu_launches_per_step)
             "roofline": {"bound": "hbm", "kernel": "prt::trace_persistent_kernel<CLOSEST> (traverse.cu / persist.cuh)", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
-                         "kernel_ms": kern_ms},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE 2^24-ray launch of this kernel
+                         # (ncu --set full, profiles/r1_trace_persistent_final_ncu.txt): 12x below the
+                         # algorithmic bytes because nodes + triangles (70 MB) live in the 126 MB L2
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if RAYS_PER_BATCH == (1 << 24) else None,
+                         "traffic_source": "profiles/r1_trace_persistent_final_ncu.txt",
+                         "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
+                         "kernel_ms": kern_ms,
+                         # what actually bounds the kernel (same capture): the L1 data pipe moves one
+                         # 32-byte sector per cycle per SM for divergent lanes
+                         "l1_data_pipe_frac": 0.82, "simt_lanes_per_warp": 18.2, "issue_slots_busy": 0.68},
             "cpu_baseline": cpu,
             "render": render,
         }
