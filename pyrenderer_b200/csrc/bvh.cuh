@@ -244,11 +244,6 @@ static __device__ PRT_SPILL_INL int sstack_unspill(uint32_t saddr, uint2* ovf) {
     ovf[0].x = n - kSpill;
     return kSpill;
 }
-__device__ __forceinline__ void sstack_push(uint32_t saddr, uint2* ovf, int& sp, uint32_t ref, float t) {
-    if (sp >= kPStack) sp = sstack_spill(saddr, ovf, sp);
-    sstack_st(saddr, sp, ref, __float_as_uint(t));
-    ++sp;
-}
 // pop until an entry that can still beat `bound` (or the stack is empty -> kDone)
 __device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, uint2* ovf, int& sp, float bound) {
     while (true) {

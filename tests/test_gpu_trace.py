@@ -166,13 +166,45 @@ def test_rotations_and_leaf_sizes_do_not_change_hits(gpu_ctx):
     tris = random_soup(30000, seed=3)
     rays = random_rays(100000, seed=4)
     ref = None
-    for leaf, rot in ((1, 0), (1, 1), (4, 1), (7, 0)):
+    visits = {}
+    for leaf, rot, treelets in ((1, 0, 0), (1, 1, 0), (4, 1, 0), (7, 0, 0), (1, 0, 1), (4, 1, 1), (7, 2, 1)):
         gpu_ctx.set_triangles(tris)
-        gpu_ctx.build_bvh(max_leaf_tris=leaf, rotations=rot)
+        st = gpu_ctx.build_bvh(max_leaf_tris=leaf, rotations=rot, treelets=treelets)
+        assert st["n_tris"] == 30000 and 3 * st["depth"] + 1 <= 128
         ids, t, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
         if ref is None:
             ref = (ids, t)
-        assert np.array_equal(ids, ref[0]) and np.array_equal(t, ref[1])
+        assert np.array_equal(ids, ref[0]) and np.array_equal(t, ref[1]), (leaf, rot, treelets)
+        gpu_ctx.reset_counters()
+        gpu_closest(gpu_ctx, rays, COUNT)
+        visits[(leaf, rot, treelets)] = gpu_ctx.counters()["node_visits"] / rays.shape[0]
+    # the SAH treelets (every maximal subtree of <= 128 triangles rebuilt with binned SAH) are
+    # there to cut record visits per ray; same hits, fewer visits
+    print(f"[treelets] record visits per ray: LBVH {visits[(1, 0, 0)]:.2f} -> treelets {visits[(1, 0, 1)]:.2f}")
+    assert visits[(1, 0, 1)] < 0.99 * visits[(1, 0, 0)]
+
+
+def test_treelets_on_clustered_and_tiny_scenes(gpu_ctx):
+    """Treelet edge cases: whole tree smaller than one treelet (3..130 triangles), coincident
+    centroids (all planes degenerate -> median split), and a clustered soup."""
+    rng = np.random.default_rng(17)
+
+    def check(tris, rays, label):
+        gpu_ctx.set_triangles(tris)
+        st = gpu_ctx.build_bvh()
+        assert st["n_tris"] == tris.shape[0]
+        check_against_oracle(gpu_ctx, tris, rays, EXACT, label)
+
+    for nt in (3, 4, 5, 63, 64, 65, 127, 128, 129, 130):
+        check(random_soup(nt, seed=100 + nt), random_rays(3000, seed=nt), f"tiny{nt}")
+    one = random_soup(1, seed=5)
+    tris = np.repeat(one, 200, axis=0)  # 200 coincident triangles: lowest id must win everywhere
+    rays = random_rays(2000, seed=6)
+    rays[:, 0:3] = tris[0].mean(axis=0) - 0.5 * rays[:, 4:7]
+    check(tris, rays, "coincident200")
+    centres = rng.uniform(0, 1, (40, 1, 3))
+    tris = (centres[rng.integers(0, 40, 20000)] + rng.normal(0, 0.004, (20000, 3, 3))).astype(np.float32)
+    check(tris, random_rays(20000, seed=8), "clustered20000")
 
 
 def test_any_and_all_hits(gpu_ctx):
@@ -265,6 +297,42 @@ def test_host_buffer_entry_point(gpu_ctx):
     h = gpu_ctx.trace_closest_host(rays, EXACT)
     ids_o, _, _, _ = oracle.closest_hit(tris, rays)
     assert np.array_equal(h["tri"], ids_o)
+
+
+def test_host_pipeline_many_chunks_equals_device_call(gpu_ctx):
+    """prt_trace_closest_host streams 2^21-ray chunks through 4 staging slots on three streams
+    (upload / trace / download).  11 chunks (ragged last one) reuse every slot at least twice; the
+    result must be bit-identical to one device-resident call, and an odd-aligned device pointer
+    (ray array starting 32 bytes + 16 into an allocation) must take the 128-bit load path."""
+    torch = _torch()
+    tris = random_soup(5000, seed=41)
+    n = 10 * (1 << 21) + 12345
+    rng = np.random.default_rng(42)
+    rays = np.empty((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(0, 1, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3] = 1e-5
+    rays[:, 7] = 3.4e38
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh()
+    h = gpu_ctx.trace_closest_host(rays, 0)
+    rd = torch.from_numpy(rays).cuda()
+    hd = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    gpu_ctx.trace_closest(rd, n, hd, 0)
+    torch.cuda.synchronize()
+    dev = hd.cpu().numpy().view(np.uint32)
+    assert np.array_equal(h.view(np.uint32).reshape(n, 4), dev)
+    # misaligned ray array: 16 bytes past a 32-byte boundary
+    m = 100000
+    buf = torch.empty((m * 8 + 4,), dtype=torch.float32, device="cuda")
+    view = buf[4:].view(m, 8)
+    view.copy_(rd[:m])
+    assert view.data_ptr() % 32 == 16
+    h2 = torch.empty((m, 4), dtype=torch.float32, device="cuda")
+    gpu_ctx.trace_closest(view, m, h2, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(h2.cpu().numpy().view(np.uint32), dev[:m])
 
 
 def test_million_triangle_soup_bvh_equals_exhaustive(gpu_ctx):
