@@ -206,6 +206,22 @@ int prt_render(prt_ctx* ctx, const prt_render_params* params, float* accum_dev,
  * (r, g, b sums, sample count).  prim_ids_dev optional [n][spp_end-spp_begin]. */
 int prt_trace_paths(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, const prt_render_params* params,
                     float* radiance_dev, int32_t* prim_ids_dev, void* stream);
+/* Path-segment log (debugging aid).  Replaces debug/ray_logger.py RayLogger.add / add_line as
+ * used by main.py:66-85 (`path_tracing(ray, a_scene, ray_logger)`).  While a log is set, every
+ * prt_render / prt_trace_paths call appends one record per traced path segment:
+ *   p0 = ray origin, p1 = hit point (or origin + 5 * direction for a miss, RayLogger.add's default
+ *   t = 5), kind = bounce index for path segments, -1 for an unoccluded light connection,
+ *   path = pixel (or ray index) * samples_in_call + sample.
+ * segments_dev: caller-owned device array of `capacity` records; count_dev: device counter the
+ * caller zeroes (it keeps counting past capacity: count > capacity means the log is truncated).
+ * NULL segments_dev switches logging off. */
+typedef struct {
+    float p0[3];
+    int32_t kind;
+    float p1[3];
+    uint32_t path;
+} prt_segment; /* 32 bytes */
+int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity, uint32_t* count_dev);
 /* same with a HOST accumulation buffer (upload, render, download; synchronous) */
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
 /* paths per wavefront wave (default 16 Mi = 2.2 GB of path state); 0 keeps the current value */

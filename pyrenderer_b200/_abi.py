@@ -61,7 +61,7 @@ EXPORTS = [
     "prt_abi_version", "prt_create", "prt_destroy", "prt_last_error", "prt_scene_set_triangles",
     "prt_scene_set_triangles_dev", "prt_bvh_build", "prt_camera_set", "prt_generate_rays",
     "prt_trace_closest", "prt_trace_any", "prt_trace_all", "prt_trace_closest_host", "prt_render", "prt_trace_paths",
-    "prt_render_host", "prt_set_wave_paths", "prt_get_counters", "prt_reset_counters",
+    "prt_render_host", "prt_set_wave_paths", "prt_set_path_log", "prt_get_counters", "prt_reset_counters",
     "prt_synchronize",
 ]
 
@@ -101,6 +101,7 @@ def load():
     lib.prt_render_host.argtypes = [vp, C.POINTER(PrtRenderParams), vp]
     lib.prt_trace_paths.argtypes = [vp, vp, u64, C.POINTER(PrtRenderParams), vp, vp, vp]
     lib.prt_set_wave_paths.argtypes = [vp, u64]
+    lib.prt_set_path_log.argtypes = [vp, vp, u64, vp]
     lib.prt_get_counters.argtypes = [vp, C.POINTER(PrtCounters)]
     lib.prt_reset_counters.argtypes = [vp]
     lib.prt_synchronize.argtypes = [vp]
@@ -248,6 +249,12 @@ class Context:
     def trace_paths(self, rays_dev, n, params, radiance_dev, prim_ids_dev=None, stream=None):
         self._check(self.lib.prt_trace_paths(self.h, _dev_ptr(rays_dev), int(n), C.byref(params),
                                              _dev_ptr(radiance_dev), _dev_ptr(prim_ids_dev), _stream_ptr(stream)))
+
+    def set_path_log(self, segments_dev=None, count_dev=None):
+        """segments_dev: torch f32 [capacity, 8] (prt_segment records), count_dev: torch i32/u32 [1];
+        None switches the log off."""
+        cap = 0 if segments_dev is None else int(segments_dev.shape[0])
+        self._check(self.lib.prt_set_path_log(self.h, _dev_ptr(segments_dev), cap, _dev_ptr(count_dev)))
 
     def render_host(self, params, accum):
         assert accum.dtype == np.float32 and accum.flags.c_contiguous

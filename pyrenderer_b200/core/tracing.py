@@ -60,7 +60,9 @@ def path_tracing(ray, a_scene, ray_logger=None, spp=1, max_depth=5, seed=1, samp
     sites main.py:22,34,78; the function itself is missing at the reference's HEAD).
     ``ray`` is one host-side Ray or a sequence of them.  Returns ``(e, r)`` with ``e + r`` the
     mean radiance of ``spp`` paths started on the ray: ``e`` = what a directly visible emitter
-    contributes, ``r`` = everything gathered after the first bounce."""
+    contributes, ``r`` = everything gathered after the first bounce.  With a ``ray_logger``
+    (debug/ray_logger.py RayLogger) every traced segment -- path segments per bounce and
+    unoccluded light connections -- is appended to it (main.py:66-85)."""
     torch = _torch()
     rays = ray if isinstance(ray, (list, tuple)) else [ray]
     rec = np.array([[*r.position, T_MIN, *r.direction, T_MAX] for r in rays], np.float32)
@@ -70,7 +72,19 @@ def path_tracing(ray, a_scene, ray_logger=None, spp=1, max_depth=5, seed=1, samp
     ids = torch.empty((len(rays), spp), dtype=torch.int32, device=d.device)
     params = ctx.render_params(seed=seed, spp_begin=sample_index, spp_end=sample_index + spp,
                                max_depth=max_depth, tmin=T_MIN, tmax=T_MAX)
-    ctx.trace_paths(d, len(rays), params, rad, ids)
+    if ray_logger is not None:
+        cap = len(rays) * spp * max_depth * 2
+        seg = torch.zeros((cap, 8), dtype=torch.float32, device=d.device)
+        cnt = torch.zeros((1,), dtype=torch.int32, device=d.device)
+        ctx.set_path_log(seg, cnt)
+    try:
+        ctx.trace_paths(d, len(rays), params, rad, ids)
+        torch.cuda.synchronize(d.device)
+    finally:
+        if ray_logger is not None:
+            ctx.set_path_log(None, None)
+    if ray_logger is not None:
+        ray_logger.add_device_segments(seg[: min(int(cnt.item()), cap)].cpu().numpy())
     out = rad.cpu().numpy().astype(np.float64)
     mean = out[:, :3] / np.maximum(out[:, 3:4], 1.0)
     lights = set(int(t) for t in a_scene.arrays()["light_tris"])

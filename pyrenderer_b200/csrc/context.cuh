@@ -53,6 +53,10 @@ struct prt_ctx {
     // wavefront state (wavefront.cu)
     void* wf = nullptr;
     uint64_t wave_paths = 16ull << 20;
+    // path-segment log (prt_set_path_log); caller-owned device memory
+    float4* log_segments = nullptr;
+    uint32_t* log_count = nullptr;
+    uint32_t log_capacity = 0;
 
     void set_error(const char* fmt, ...) {
         va_list ap;

@@ -342,6 +342,18 @@ int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_
     return PRT_OK;
 }
 
+int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity, uint32_t* count_dev) {
+    CHECK_CTX(ctx);
+    if (segments_dev && (!count_dev || capacity == 0 || capacity > 0xffffffffull)) {
+        ctx->set_error("path log: need a counter and 0 < capacity < 2^32");
+        return PRT_ERR_INVALID;
+    }
+    ctx->log_segments = (float4*)segments_dev;
+    ctx->log_count = segments_dev ? count_dev : nullptr;
+    ctx->log_capacity = segments_dev ? (uint32_t)capacity : 0u;
+    return PRT_OK;
+}
+
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths) {
     CHECK_CTX(ctx);
     if (paths) ctx->wave_paths = paths;

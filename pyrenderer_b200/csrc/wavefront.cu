@@ -60,7 +60,20 @@ struct WaveParams {
     uint32_t rr_start;
     float3 light_color;
     float tmin, tmax;
+    // path-segment log (prt_set_path_log): nullptr = off
+    float4* log;
+    uint32_t* log_count;
+    uint32_t log_capacity;
 };
+
+// one record = 2 x float4: (p0, kind), (p1, path)
+__device__ __forceinline__ void log_segment(const WaveParams& P, float3 p0, float3 p1, int kind, uint32_t path) {
+    const uint32_t i = atomicAdd(P.log_count, 1u);
+    if (i < P.log_capacity) {
+        P.log[2 * (size_t)i] = make_float4(p0.x, p0.y, p0.z, __int_as_float(kind));
+        P.log[2 * (size_t)i + 1] = make_float4(p1.x, p1.y, p1.z, __uint_as_float(path));
+    }
+}
 
 __device__ __forceinline__ void camera_ray(const CamDev& cam, double u, double v, float4& ro,
                                            float4& rd, float tmin, float tmax) {
@@ -166,6 +179,7 @@ struct QueueShadowIO {
     const float4* srays;
     const float4* scontrib;
     float4* L;
+    const WaveParams* P;  // kernel parameter space; read only when the path log is on
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         tag = k;
         ldg256_cs(srays + 2 * (size_t)k, ro, rd);
@@ -176,15 +190,21 @@ struct QueueShadowIO {
             uint32_t pid = __float_as_uint(c.w);
             float4 l = L[pid];
             L[pid] = make_float4(l.x + c.x, l.y + c.y, l.z + c.z, 0.f);
+            if (P->log) {  // unoccluded light connection: RayLogger.add_line(p, p_light)
+                const float4 ro = srays[2 * (size_t)tag], rd = srays[2 * (size_t)tag + 1];
+                const uint32_t pixel = pid % P->npix, s = P->s_begin + pid / P->npix;
+                log_segment(*P, xyz(ro), xyz(ro) + xyz(rd) * (rd.w / (1.0f - 1e-4f)), -1,
+                            pixel * P->ns_total + (s - P->spp_begin));
+            }
         }
     }
 };
 
 __global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
-shadow_kernel(SceneDev sc, const float4* __restrict__ srays, const float4* __restrict__ scontrib,
-              float4* L, unsigned int* cnt) {
+shadow_kernel(SceneDev sc, const __grid_constant__ WaveParams P, const float4* __restrict__ srays,
+              const float4* __restrict__ scontrib, float4* L, unsigned int* cnt) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
-    QueueShadowIO io{srays, scontrib, L};
+    QueueShadowIO io{srays, scontrib, L, &P};
     trace_persistent<MODE_ANY, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
 }
 
@@ -235,6 +255,11 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
             uint32_t pixel = pid % P.npix, s = P.s_begin + pid / P.npix;
             if (bounce == 0 && prim_ids)
                 prim_ids[(size_t)pixel * P.ns_total + (s - P.spp_begin)] = gid;
+            if (P.log) {  // debug/ray_logger.py: origin -> hit point, or 5 units along a ray that escapes
+                const float3 lo3 = xyz(ro), ld3 = xyz(rd);
+                const float tl = gid >= 0 ? h.x : 5.0f;
+                log_segment(P, lo3, lo3 + ld3 * tl, (int)bounce, pixel * P.ns_total + (s - P.spp_begin));
+            }
             if (gid >= 0) {
                 float3 o = xyz(ro), d = xyz(rd);
                 float4 sh = __ldg(sc.shade + gid);
@@ -493,6 +518,7 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
     P.rr_start = p->rr_start;
     P.light_color = make_float3(p->light_color[0], p->light_color[1], p->light_color[2]);
     P.tmin = p->tmin; P.tmax = p->tmax;
+    P.log = ctx->log_segments; P.log_count = ctx->log_count; P.log_capacity = ctx->log_capacity;
     for (uint32_t s = p->spp_begin; s < p->spp_end; s += (uint32_t)per_wave) {
         P.s_begin = s;
         P.ns_wave = (uint32_t)((p->spp_end - s) < per_wave ? (p->spp_end - s) : per_wave);
@@ -517,7 +543,7 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
             else
                 shade_kernel<false><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
                                                                        w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
-            shadow_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->srays, w->scontrib, w->L, w->cnt);
+            shadow_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt);
             advance_kernel<<<1, 1, 0, stream>>>(w->cnt, ctx->counters);
         }
         accumulate_kernel<<<(P.npix + 255) / 256, 256, 0, stream>>>(w->L, P.npix, P.ns_wave, (float4*)accum, ctx->counters);

@@ -80,6 +80,31 @@ def main_progressive(scene_file=DEFAULT_SCENE, iterations=1001, max_depth=16, se
     return accum
 
 
+def main_debug(scene_file=DEFAULT_SCENE, step=10, samples=6, max_depth=5, seed=1, out="rays.obj", device=0):
+    """The reference's main_debug (main.py:66-85): 6 jittered camera rays through every 10th
+    pixel, traced with a RayLogger; the logged segments go to a Wavefront OBJ of line elements
+    instead of an Open3D window."""
+    import random
+    from .debug.ray_logger import RayLogger
+    a_scene, a_camera = read_file(scene_file)
+    x_dim, y_dim = a_camera.get_resolution()
+    rng = random.Random(seed)
+    rays = []
+    for i in range(0, x_dim, step):
+        for j in range(0, y_dim, step):
+            for _ in range(samples):
+                x = (i + rng.random()) / float(x_dim)
+                y = (j + rng.random()) / float(y_dim)
+                rays.append(a_camera.generate_ray(np.array([x, y])))
+    ray_logger = RayLogger()
+    tracing.path_tracing(rays, a_scene, ray_logger, spp=1, max_depth=max_depth, seed=seed, device=device)
+    if out:
+        ray_logger.write_obj(out)
+    print(f"{len(rays)} paths, {len(ray_logger.lines)} segments"
+          f" ({sum(1 for k in ray_logger.kinds if k < 0)} light connections)")
+    return ray_logger
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--scene", default=DEFAULT_SCENE)
@@ -94,7 +119,12 @@ if __name__ == "__main__":
                     help="main_taichi.py-style loop: N iterations of 1 spp into one buffer")
     ap.add_argument("--physical", action="store_true",
                     help="physically-based estimator (scene emission + MIS) instead of the reference's")
+    ap.add_argument("--debug-rays", metavar="OBJ", default=None,
+                    help="main_debug: log the segments of a sparse set of camera paths to a Wavefront OBJ")
     a = ap.parse_args()
+    if a.debug_rays:
+        main_debug(a.scene, max_depth=a.max_depth, seed=a.seed, out=a.debug_rays)
+        raise SystemExit(0)
     if a.progressive:
         main_progressive(a.scene, a.progressive, a.max_depth, a.seed, a.out)
         raise SystemExit(0)

@@ -268,3 +268,35 @@ def test_path_tracing_drop_in(cornell):
     assert np.all(e == 0) and np.all(r > 0) and np.isfinite(r).all()
     es, rs = tracing.path_tracing([cam.generate_ray(np.array([u, 0.5])) for u in (0.1, 0.5, 0.9)], scene, spp=16)
     assert es.shape == (3, 3) and rs.shape == (3, 3) and np.all(es + rs > 0)
+
+
+def test_path_log_segments_form_paths(cornell):
+    """prt_set_path_log through path_tracing(ray, scene, ray_logger) (main.py:66-85): every path is
+    a chain -- segment k+1 starts where segment k ends, the first one starts at the camera --, the
+    number of path segments equals the closest-hit rays traced, light connections end on the light."""
+    from pyrenderer_b200.core import tracing
+    from pyrenderer_b200.debug.ray_logger import RayLogger
+    scene, cam = cornell
+    rng = np.random.default_rng(3)
+    rays = [cam.generate_ray(rng.uniform(0.05, 0.95, 2)) for _ in range(200)]
+    ctx = scene.commit(0)
+    ctx.reset_counters()
+    lg = RayLogger()
+    e, r = tracing.path_tracing(rays, scene, lg, spp=2, max_depth=4, seed=5)
+    c = ctx.counters()
+    kinds, paths = np.array(lg.kinds), np.array(lg.paths)
+    P = np.array(lg.points).reshape(-1, 2, 3)
+    assert (kinds >= 0).sum() == c["rays_closest"] and (kinds < 0).sum() > 50 and (kinds < 0).sum() <= c["rays_shadow"]
+    assert set(np.unique(paths)) == set(range(400))
+    eye = np.array([0.0, 1.0, 6.8])
+    for p in range(400):
+        seg = P[(paths == p) & (kinds >= 0)]
+        k = kinds[(paths == p) & (kinds >= 0)]
+        assert list(k) == list(range(len(k))) and np.allclose(seg[0, 0], eye, atol=1e-6)
+        assert np.allclose(seg[1:, 0], seg[:-1, 1], atol=2e-5)   # o + t*d vs the barycentric hit point
+    ends = P[kinds < 0][:, 1]
+    assert np.allclose(ends[:, 1], 1.98, atol=1e-3) and np.all(np.abs(ends[:, 0] + 0.005) <= 0.236) and np.all(np.abs(ends[:, 2] + 0.03) <= 0.191)
+    assert e.shape == (200, 3) and np.isfinite(r).all()
+    # logging is off again: a second call leaves a fresh logger empty-handed only if asked without one
+    e2, r2 = tracing.path_tracing(rays, scene, None, spp=2, max_depth=4, seed=5)
+    assert np.array_equal(e, e2) and np.array_equal(r, r2)

@@ -243,3 +243,28 @@ def test_tungsten_mesh_primitive(tmp_path):
     c = a["tris"][:12].mean(axis=1) - np.array([2, 3, 4])
     assert np.all(np.einsum("ij,ij->i", a["normals"][:12], c) > 0)
     assert cam.aspect_ratio == 2.0
+
+
+def test_ray_logger_container(tmp_path):
+    """debug/ray_logger.py:1-16: points / lines / colors grow as in the reference; device records
+    are appended in (path, bounce, light connection last) order; OBJ export has one `l` per line."""
+    from pyrenderer_b200.core.ray import Ray
+    from pyrenderer_b200.debug.ray_logger import BOUNCE_COLORS, LIGHT_COLOR, RayLogger
+    lg = RayLogger()
+    lg.add(Ray(np.array([0.0, 1.0, 2.0]), np.array([0.0, 0.0, -1.0])), t=5, color=[0, 1, 0])
+    lg.add_line([0, 0, 0], [1, 1, 1])
+    assert len(lg.points) == 4 and lg.lines == [[0, 1], [2, 3]] and lg.colors == [[0, 1, 0], [1, 0, 0]]
+    assert np.allclose(lg.points[1], [0, 1, -3])
+    rec = np.zeros((4, 8), np.float32)
+    kinds = np.array([1, -1, 0, 0], np.int32)
+    paths = np.array([7, 7, 7, 3], np.uint32)
+    rec[:, 3] = kinds.view(np.float32)
+    rec[:, 7] = paths.view(np.float32)
+    rec[:, 0] = np.arange(4)
+    lg.add_device_segments(rec)
+    assert lg.paths[2:] == [3, 7, 7, 7] and lg.kinds[2:] == [0, 0, 1, -1]
+    assert lg.colors[-1] == LIGHT_COLOR and lg.colors[-2] == BOUNCE_COLORS[1]
+    out = tmp_path / "rays.obj"
+    lg.write_obj(str(out))
+    text = out.read_text().splitlines()
+    assert sum(l.startswith("v ") for l in text) == 12 and sum(l.startswith("l ") for l in text) == 6
