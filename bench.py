@@ -332,6 +332,34 @@ def main():
                   "rays_shadow_per_step": rc["rays_shadow"] / args.steps,
                   "e2e_host_ms_per_step": r_e2e_ms, "e2e_spp_per_s": spp / (r_e2e_ms * 1e-3),
                   "gpu_launches_per_step": launches_render}
+        # BASELINE configs[0] -- the reference's own CPU-runnable case: Cornell 256x256, 16 spp, depth 5.
+        # GPU through the same C-ABI call; CPU = oracle port of main.py's loop (all host threads);
+        # same seed => same paths, so the two images are also a parity spot check.
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            import oracle
+            w1 = h1 = 256
+            rctx.set_camera(iview, sh * (w1 / h1), sh, focal, w1, h1)
+            kw = dict(seed=1, spp_begin=0, spp_end=16, max_depth=5)
+            acc1 = torch.zeros((h1, w1, 4), dtype=torch.float32, device=dev)
+            rctx.render(rctx.render_params(**kw), acc1)  # warm
+            acc1.zero_()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            rctx.render(rctx.render_params(**kw), acc1)
+            g1.record()
+            torch.cuda.synchronize()
+            c1_gpu_ms = g0.elapsed_time(g1)
+            ocam = oracle.make_camera(iview, sh * (w1 / h1), sh, focal, w1, h1)
+            t0 = time.perf_counter()
+            acc_o = oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"], ocam,
+                                  oracle.make_params(**kw))[0]
+            c1_cpu_ms = (time.perf_counter() - t0) * 1e3
+            g = acc1.cpu().numpy().astype(np.float64)[..., :3]
+            c1 = {"workload": "cornell-box 256x256, 16 spp, max depth 5 (BASELINE configs[0])",
+                  "gpu_ms": c1_gpu_ms, "gpu_spp_per_s": 16 / (c1_gpu_ms * 1e-3),
+                  "cpu_port_ms": c1_cpu_ms, "cpu_port_spp_per_s": 16 / (c1_cpu_ms * 1e-3), "cpu_cores": oracle.num_threads(),
+                  "rel_rmse_gpu_vs_oracle_equal_seed": float(np.sqrt(np.mean((g - acc_o[..., :3]) ** 2)) / np.mean(acc_o[..., :3]))}
+            render["c1"] = c1
         rctx.close()
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1)
@@ -339,7 +367,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         import oracle
         cores = oracle.num_threads()
-        n = max(256, 24 * cores)
+        n = max(256, 192 * cores)  # ~10-15 s of brute force on the box's host cores
         sample = host_rays(n, seed=99)
         oracle.closest_hit(tris[:1000], sample[:8])
         t0 = time.perf_counter()

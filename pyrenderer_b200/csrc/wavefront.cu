@@ -175,11 +175,12 @@ closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
 }
 
 // shadow rays: an unoccluded ray adds its pending NEE contribution to the path's radiance
+template <bool LOG>
 struct QueueShadowIO {
     const float4* srays;
     const float4* scontrib;
     float4* L;
-    const WaveParams* P;  // kernel parameter space; read only when the path log is on
+    const WaveParams* P;  // kernel parameter space; LOG only
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         tag = k;
         ldg256_cs(srays + 2 * (size_t)k, ro, rd);
@@ -190,7 +191,7 @@ struct QueueShadowIO {
             uint32_t pid = __float_as_uint(c.w);
             float4 l = L[pid];
             L[pid] = make_float4(l.x + c.x, l.y + c.y, l.z + c.z, 0.f);
-            if (P->log) {  // unoccluded light connection: RayLogger.add_line(p, p_light)
+            if (LOG) {  // unoccluded light connection: RayLogger.add_line(p, p_light)
                 const float4 ro = srays[2 * (size_t)tag], rd = srays[2 * (size_t)tag + 1];
                 const uint32_t pixel = pid % P->npix, s = P->s_begin + pid / P->npix;
                 log_segment(*P, xyz(ro), xyz(ro) + xyz(rd) * (rd.w / (1.0f - 1e-4f)), -1,
@@ -200,11 +201,14 @@ struct QueueShadowIO {
     }
 };
 
+// LOG: the path-segment log (prt_set_path_log) is a separate instantiation, so the production
+// kernels carry none of it (as a run-time flag it cost the Cornell render 9 %)
+template <bool LOG>
 __global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 shadow_kernel(SceneDev sc, const __grid_constant__ WaveParams P, const float4* __restrict__ srays,
               const float4* __restrict__ scontrib, float4* L, unsigned int* cnt) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
-    QueueShadowIO io{srays, scontrib, L, &P};
+    QueueShadowIO<LOG> io{srays, scontrib, L, &P};
     trace_persistent<MODE_ANY, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
 }
 
@@ -226,7 +230,7 @@ __device__ __forceinline__ float tri_area_gid(const SceneDev& sc, uint32_t gid) 
 // sampling are weighted with the power heuristic (the scheme of the reference's draft
 // sample_direct_lighting2, core/tracing.py:56-90), the path ends on an emitter.  beta.w carries
 // the solid-angle pdf of the BSDF sample that produced the current ray (< 0: camera / specular).
-template <bool PHYS>
+template <bool PHYS, bool LOG>
 __global__ void __launch_bounds__(256)
 shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, float4* rays,
              const float4* __restrict__ hits, float4* beta, float4* L, float4* srays,
@@ -255,7 +259,7 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
             uint32_t pixel = pid % P.npix, s = P.s_begin + pid / P.npix;
             if (bounce == 0 && prim_ids)
                 prim_ids[(size_t)pixel * P.ns_total + (s - P.spp_begin)] = gid;
-            if (P.log) {  // debug/ray_logger.py: origin -> hit point, or 5 units along a ray that escapes
+            if (LOG) {  // debug/ray_logger.py: origin -> hit point, or 5 units along a ray that escapes
                 const float3 lo3 = xyz(ro), ld3 = xyz(rd);
                 const float tl = gid >= 0 ? h.x : 5.0f;
                 log_segment(P, lo3, lo3 + ld3 * tl, (int)bounce, pixel * P.ns_total + (s - P.spp_begin));
@@ -489,7 +493,7 @@ static int wave_alloc(prt_ctx* ctx, uint64_t cap) {
     w->cap = cap;
     int bt = 0, bs = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, closest_kernel, kTraceThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, shade_kernel<false>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, shade_kernel<false, false>, 256, 0);
     w->grid_trace = ctx->num_sms * (bt > 0 ? bt : 4);
     w->grid_shade = ctx->num_sms * (bs > 0 ? bs : 4);
     return PRT_OK;
@@ -537,13 +541,14 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
             } else {
                 closest_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt);
             }
-            if (p->flags & PRT_RENDER_PHYSICAL)
-                shade_kernel<true><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
-                                                                      w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
-            else
-                shade_kernel<false><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, w->beta, w->L,
-                                                                       w->srays, w->scontrib, qin, qout, w->cnt, prim_ids);
-            shadow_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt);
+            const bool phys = p->flags & PRT_RENDER_PHYSICAL, logging = P.log != nullptr;
+#define PRT_SHADE(PH, LG) shade_kernel<PH, LG><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, \
+                                                  w->beta, w->L, w->srays, w->scontrib, qin, qout, w->cnt, prim_ids)
+            if (logging) { if (phys) PRT_SHADE(true, true); else PRT_SHADE(false, true); }
+            else { if (phys) PRT_SHADE(true, false); else PRT_SHADE(false, false); }
+#undef PRT_SHADE
+            if (logging) shadow_kernel<true><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt);
+            else shadow_kernel<false><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt);
             advance_kernel<<<1, 1, 0, stream>>>(w->cnt, ctx->counters);
         }
         accumulate_kernel<<<(P.npix + 255) / 256, 256, 0, stream>>>(w->L, P.npix, P.ns_wave, (float4*)accum, ctx->counters);
