@@ -1,13 +1,15 @@
 // bvh.cuh -- the quantised 4-wide node, its slab test and the per-lane stack.
 //
 // Node64 (common.cuh) holds the boxes of up to FOUR children, quantised to 8 bits per
-// plane in the node's own frame: plane = o + q * scale, scale a power of two per axis.  The builder (bvh_build.cu)
-// rounds lo down / hi up against this exact decode expression, so a decoded box always
-// contains the child's true FP32 box.  The slab test never decodes a box: per axis it
-// forms a = scale/d and b = (o - ray.o)/d once and each of the 24 planes costs one
-// I2F.U8 + one FMA (t = q*a + b).  Planes are stored as one word of four "lo" bytes and
-// one word of four "hi" bytes per axis; the ray's octant picks which word is the near
-// side, so no per-plane min/max is needed.
+// plane in the node's own frame: plane = o + q * scale, scale a power of two per axis.
+// The builder (bvh_build.cu) rounds lo down / hi up against this exact decode expression,
+// so a decoded box always contains the child's true FP32 box.  The slab test never
+// decodes a box: per axis it forms a = scale/d and b = (o - ray.o)/d once; a plane then
+// costs one byte->float conversion (I2F.U8 on the XU pipe, or a folded PRMT on the ALU
+// pipe, PlaneEval) and half a packed FFMA2 (t = q*a + b for two children at once).
+// Planes are stored as one word of four "lo" bytes and one word of four "hi" bytes per
+// axis; the ray's octant picks which word is the near side, so no per-plane min/max is
+// needed.  The node is fetched with two 256-bit loads (ldg_node).
 //
 // Child references are explicit (record index, or kLeafFlag | first_tri << 3 | count for
 // a leaf of 1..7 triangles stored contiguously, or kNoChild).

@@ -1,19 +1,20 @@
 // persist.cuh -- persistent-warp FP32 traversal with lane-level dynamic ray fetch
 // and deferred leaves.
 //
-// Incoherent rays have very different traversal lengths (soup-1M: mean 83 record
-// visits, ~3 leaf visits, long tail).  With one ray per thread a warp runs until its
-// LONGEST ray ends and every leaf visit stalls the 31 other lanes: ncu measured 6.7
-// of 32 lanes active (profiles/r1_trace_kernel_ncu.txt).  Here
+// Incoherent rays have very different traversal lengths (soup-1M: mean 38 record
+// visits of a 4-wide node, ~5 leaf visits, long tail).  With one ray per thread a warp
+// runs until its LONGEST ray ends and every leaf visit stalls the 31 other lanes: ncu
+// measured 6.7 of 32 lanes active (profiles/r1_trace_kernel_ncu.txt).  Here
 //   * warps are persistent: when `refill_idle` or more lanes hold no ray, the idle
-//     lanes pull new rays from a global counter (one atomic per warp, ballot +
-//     prefix popcount for the slot) -- Aila & Laine, "Understanding the efficiency
-//     of ray traversal on GPUs" (HPG 2009);
-//   * every loop iteration is ONE record visit for the lanes that are at an internal
-//     record; a lane that reaches a leaf parks until `leaf_batch` lanes are parked
-//     (or nobody has records left), then the parked lanes intersect their leaves
-//     together.  Record visits are >90 % of the instructions, so they are what is
-//     kept convergent.
+//     lanes take new ray indices from the warp's reservation (chunks of the global
+//     counter, one atomic per chunk, requested one chunk ahead; ballot + prefix
+//     popcount for the slot) -- Aila & Laine, "Understanding the efficiency of ray
+//     traversal on GPUs" (HPG 2009);
+//   * every loop iteration is PRT_VISITS_PER_ITER record visits for the lanes that
+//     are at an internal record; a lane that reaches a leaf parks until `leaf_batch`
+//     lanes are parked (or nobody has records left), then the parked lanes intersect
+//     their leaves together.  Record visits are 60 % of the issued instructions and
+//     run at 19..26 of 32 lanes; they are what is kept convergent.
 //
 // IO is a functor: load(k, ro, rd, tag) / store(tag, t, u, v, gid); it binds this
 // loop to the API ray arrays or to the wavefront queues.
