@@ -192,6 +192,7 @@ struct TreeletShared {
     float lo[kTreelet][3], hi[kTreelet][3];   // triangle boxes
     uint32_t tri[kTreelet];                   // triangle ids (vals entries)
     uint8_t order[kTreelet], tmp[kTreelet];   // permutation being partitioned
+    uint32_t pk[kTreelet];                    // per position of the current range: bin per axis, 8 bits each
     int names[kTreelet];                      // internal node names available to this subtree; [0] = root
     int stack[kTreelet][3];                   // begin, end, name
 };
@@ -206,7 +207,7 @@ __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
 // scans inside an NB-lane group; candidate plane j = "bins <= j go left".  NB = 16: two rounds
 // (axes x,y then z); NB = 8: the 24 (axis, bin) pairs fit one round.  Returns cost (inf: none).
 template <int NB>
-__device__ __forceinline__ float treelet_best_split(const TreeletShared& S, int b, int e, const float cmin[3],
+__device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int e, const float cmin[3],
                                                     const float scale[3], int lane, int& best_slot) {
     const unsigned FULL = 0xffffffffu;
     const float inf = __int_as_float(0x7f800000);
@@ -214,19 +215,31 @@ __device__ __forceinline__ float treelet_best_split(const TreeletShared& S, int 
     constexpr int kRounds = NB == 16 ? 2 : 1;
     float best = inf;
     best_slot = -1;
+    // bins of every triangle of the range, one triangle per lane
+    for (int k = b + lane; k < e; k += 32) {
+        const int q = S.order[k];
+        uint32_t pk = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int j = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cmin[a]) * scale[a]);
+            j = j > NB - 1 ? NB - 1 : j;
+            pk |= (uint32_t)j << (8 * a);
+        }
+        S.pk[k] = pk;
+    }
+    __syncwarp();
 #pragma unroll
     for (int round = 0; round < kRounds; ++round) {
         const int a = lane / NB + kAxesPerRound * round, bin = lane % NB;
-        const float cm_a = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);  // selects: no dynamic indexing
         const float sc_a = a == 0 ? scale[0] : (a == 1 ? scale[1] : (a == 2 ? scale[2] : 0.0f));
         float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
         int cnt = 0;
         if (sc_a > 0.0f) {
+            const uint32_t want = (uint32_t)bin << (8 * a), mask = 0xffu << (8 * a);
+#pragma unroll 4
             for (int k = b; k < e; ++k) {
-                const int q = S.order[k];
-                int j = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
-                j = j > NB - 1 ? NB - 1 : j;
-                if (j == bin) {
+                if ((S.pk[k] & mask) == want) {
+                    const int q = S.order[k];
                     l0 = fminf(l0, S.lo[q][0]); l1 = fminf(l1, S.lo[q][1]); l2 = fminf(l2, S.lo[q][2]);
                     h0 = fmaxf(h0, S.hi[q][0]); h1 = fmaxf(h1, S.hi[q][1]); h2 = fmaxf(h2, S.hi[q][2]);
                     ++cnt;
@@ -344,8 +357,6 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                 else treelet_best_split<8>(S, b, e, cmin, scale, lane, best_slot);
                 if (best_slot >= 0) {
                     const int a = best_slot / nb, j = best_slot % nb;
-                    const float cm_a = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);
-                    const float sc_a = a == 0 ? scale[0] : (a == 1 ? scale[1] : scale[2]);
                     // stable partition of order[b, e) by bin <= j
                     int nleft = 0;
                     for (int k0 = b; k0 < e; k0 += 32) {
@@ -354,9 +365,7 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                         int q = 0;
                         if (k < e) {
                             q = S.order[k];
-                            int bj = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
-                            bj = bj > nb - 1 ? nb - 1 : bj;
-                            go_left = bj <= j;
+                            go_left = (int)((S.pk[k] >> (8 * a)) & 0xffu) <= j;
                         }
                         const unsigned lm = __ballot_sync(FULL, go_left);
                         if (go_left) S.tmp[b + nleft + __popc(lm & ((1u << lane) - 1u))] = (uint8_t)q;
@@ -369,9 +378,7 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                         int q = 0;
                         if (k < e) {
                             q = S.order[k];
-                            int bj = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cm_a) * sc_a);
-                            bj = bj > nb - 1 ? nb - 1 : bj;
-                            go_right = bj > j;
+                            go_right = (int)((S.pk[k] >> (8 * a)) & 0xffu) > j;
                         }
                         const unsigned rm = __ballot_sync(FULL, go_right);
                         if (go_right) S.tmp[b + nleft + nright + __popc(rm & ((1u << lane) - 1u))] = (uint8_t)q;
