@@ -207,6 +207,41 @@ def test_treelets_on_clustered_and_tiny_scenes(gpu_ctx):
     check(tris, random_rays(20000, seed=8), "clustered20000")
 
 
+def test_deep_stacks_spill_and_unspill(gpu_ctx):
+    """4000 large triangles that all overlap: nearly every child box is hit at every level, so the
+    per-lane stacks grow far past the 16 shared-memory levels and exercise the spill / unspill
+    path (bvh.cuh sstack_spill) in every kernel family: persistent closest / any (plain FP32),
+    one-ray-per-thread exact closest, all-hits (never culls: deepest) -- all against the oracle."""
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    c = rng.uniform(0.3, 0.7, (4000, 1, 3))
+    tris = (c + rng.uniform(-0.6, 0.6, (4000, 3, 3))).astype(np.float32)
+    rays = random_rays(6000, seed=78)
+    gpu_ctx.set_triangles(tris)
+    st = gpu_ctx.build_bvh(max_leaf_tris=1)
+    assert 3 * st["depth"] + 1 <= 128
+    ids_o, t_o, _, _ = oracle.closest_hit(tris, rays)
+    cnt_o, sums_o = oracle.all_hits(tris, rays)
+    occ_o = oracle.any_hit(tris, rays)
+    assert cnt_o.mean() > 100  # every ray crosses hundreds of triangles
+    check_against_oracle(gpu_ctx, tris, rays, EXACT, "overlap4000", ref=oracle.closest_hit(tris, rays))
+    r = torch.from_numpy(rays).cuda()
+    cnt = torch.empty(rays.shape[0], dtype=torch.int32, device="cuda")
+    sums = torch.empty(rays.shape[0], dtype=torch.int64, device="cuda")
+    occ = torch.empty(rays.shape[0], dtype=torch.uint8, device="cuda")
+    gpu_ctx.trace_all(r, rays.shape[0], cnt, sums, EXACT)
+    gpu_ctx.trace_any(r, rays.shape[0], occ, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o) and np.array_equal(sums.cpu().numpy().view(np.uint64), sums_o)
+    assert np.mean(occ.cpu().numpy() != occ_o) < 1e-3
+    ids_f, t_f, _, _ = gpu_closest(gpu_ctx, rays, 0)  # persistent kernel, plain FP32
+    frac = np.mean(ids_f != ids_o)
+    print(f"[overlap4000] mean hits per ray {cnt_o.mean():.0f}, FP32-only closest id mismatch fraction {frac:.2e}")
+    assert frac < 2e-3
+    same = ids_f == ids_o
+    assert np.abs(t_f[same & (ids_o >= 0)] - t_o[same & (ids_o >= 0)]).max() < 1e-4
+
+
 def test_any_and_all_hits(gpu_ctx):
     torch = _torch()
     tris = random_soup(3000, seed=9)
