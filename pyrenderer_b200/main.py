@@ -35,6 +35,32 @@ def write_png(path, rgb8):
                 + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
+def write_hdr(path, img):
+    """Linear radiance, top row first, to ``.pfm`` (Portable Float Map, written here) or ``.exr``
+    (through OpenCV when it is built with OpenEXR) -- the HDR half of SURVEY 8f rank 2; the
+    reference only ever writes the 8-bit image (main.py:57-59)."""
+    img = np.ascontiguousarray(img, np.float32)
+    if path.lower().endswith(".pfm"):
+        h, w, _ = img.shape
+        with open(path, "wb") as f:
+            f.write(f"PF\n{w} {h}\n-1.0\n".encode())  # negative scale = little endian
+            f.write(img[::-1].tobytes())                 # PFM stores the bottom row first
+        return
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    if not cv2.imwrite(path, img[:, :, ::-1]):
+        raise OSError(f"could not write {path}")
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"PF"
+        w, h = (int(x) for x in f.readline().split())
+        scale = float(f.readline())
+        data = np.frombuffer(f.read(), "<f4" if scale < 0 else ">f4").reshape(h, w, 3)
+    return np.ascontiguousarray(data[::-1])
+
+
 def main(scene_file=DEFAULT_SCENE, samples=8, max_depth=5, width=None, height=None, seed=1,
          out="test.png", tonemap=None, device=0, physical=False):
     a_scene, a_camera = read_file(scene_file)
@@ -47,7 +73,9 @@ def main(scene_file=DEFAULT_SCENE, samples=8, max_depth=5, width=None, height=No
     torch.cuda.synchronize()
     dt = time.time() - t0
     image = tracing.to_uint8(tracing.to_image(accum, tonemap))
-    if out:
+    if out and out.lower().endswith((".pfm", ".exr")):
+        write_hdr(out, tracing.to_image(accum, None))
+    elif out:
         write_png(out, image)
     c = a_scene.commit(device).counters()
     rays = c["rays_closest"] + c["rays_shadow"]

@@ -268,3 +268,16 @@ def test_ray_logger_container(tmp_path):
     lg.write_obj(str(out))
     text = out.read_text().splitlines()
     assert sum(l.startswith("v ") for l in text) == 12 and sum(l.startswith("l ") for l in text) == 6
+
+
+def test_hdr_output_roundtrip(tmp_path):
+    """SURVEY 8f rank 2, HDR half: linear radiance survives a .pfm round trip bit for bit (values
+    above 1 included), top row first on both sides."""
+    from pyrenderer_b200.main import read_pfm, write_hdr
+    rng = np.random.default_rng(2)
+    img = (rng.uniform(0, 20, (7, 5, 3))).astype(np.float32)
+    p = str(tmp_path / "x.pfm")
+    write_hdr(p, img)
+    assert np.array_equal(read_pfm(p), img)
+    head = open(p, "rb").read(12)
+    assert head.startswith(b"PF\n5 7\n")
