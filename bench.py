@@ -142,7 +142,7 @@ def run_reference(args):
     import oracle
     tris = soup(SOUP_TRIS)
     cores = oracle.num_threads()
-    n = max(64, 8 * cores)  # rays per step: ~n * 1e6 triangle tests
+    n = max(64, 64 * cores)  # rays per step (~1 s of brute force per step with every thread busy)
     times = []
     for s in range(args.warmup + args.steps):
         rays = host_rays(n, seed=1000 + s)
@@ -367,7 +367,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         import oracle
         cores = oracle.num_threads()
-        n = max(256, 192 * cores)  # ~10-15 s of brute force on the box's host cores
+        n = max(256, 640 * cores)  # ~10-15 s of brute force with every host thread busy
         sample = host_rays(n, seed=99)
         oracle.closest_hit(tris[:1000], sample[:8])
         t0 = time.perf_counter()

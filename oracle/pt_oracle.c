@@ -257,7 +257,7 @@ int orc_closest_hit(const float* tris, uint32_t nt, const float* rays, uint64_t 
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 4)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const float* r = rays + (size_t)i * 8;
         double o[3] = {r[0], r[1], r[2]}, d[3] = {r[4], r[5], r[6]};
@@ -279,7 +279,7 @@ int orc_any_hit(const float* tris, uint32_t nt, const float* rays, uint64_t n, u
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 4)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const float* r = rays + (size_t)i * 8;
         double o[3] = {r[0], r[1], r[2]}, d[3] = {r[4], r[5], r[6]};
