@@ -61,6 +61,18 @@ def main():
                     ms.append(ctx.build_bvh(treelets=tl, rotations=rot)["ms_total"])
                 m, nn, nt = measure(ctx, r, hits)
                 print(f"treelets {tl} rotations {rot}: {m:8.1f} Mrays/s  N_node {nn:6.2f} N_tri {nt:5.2f} nodes {st['n_nodes']} depth {st['depth']} sah {st['sah_cost']:.1f} build {np.median(ms):.2f} ms (hierarchy+treelets {st['ms_hierarchy']:.2f})", flush=True)
+    elif mode == "any":
+        ctx = _abi.Context(0)
+        ctx.set_triangles_dev(tris, 1_000_000); ctx.build_bvh()
+        occ = torch.empty(N, dtype=torch.uint8, device=dev)
+        for tmax in (0.05, 0.2, 3.4e38):
+            r[:, 7] = tmax
+            best = 1e9
+            for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); ctx.trace_any(r, N, occ, 0); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            print(f"any-hit soup-1M tmax {tmax:g}: {N / best / 1e3:8.1f} Mrays/s  occluded {occ.float().mean().item():.3f}", flush=True)
     elif mode == "util":
         ctx = _abi.Context(0)
         ctx.set_triangles_dev(tris, 1_000_000)

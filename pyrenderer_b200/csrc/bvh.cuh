@@ -301,4 +301,26 @@ __device__ __forceinline__ uint32_t descend(NodeHits& h, uint32_t saddr, uint2* 
     return h.ref[0];
 }
 
+// Any-hit traversal needs no order: all four children are stored unconditionally (the stack
+// pointer advances past the hit ones) and the top is popped back -- no sorting network, no
+// +inf selects, no culling on pop (an entry's distance was <= tmax when it was pushed and tmax
+// never shrinks).  37 instead of 66 instructions of bookkeeping per visit.
+__device__ __forceinline__ uint32_t descend_any(const NodeHits& h, uint32_t saddr, uint2* ovf, int& sp) {
+    const float inf = __int_as_float(0x7f800000);
+    if (sp > kPStack - 4) sp = sstack_spill(saddr, ovf, sp);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        sstack_st(saddr, sp, h.ref[c], __float_as_uint(h.t[c]));
+        sp += h.t[c] < inf ? 1 : 0;
+    }
+    if (sp == 0) {
+        sp = sstack_unspill(saddr, ovf);
+        if (sp == 0) return kDone;
+    }
+    --sp;
+    uint32_t ref, tb;
+    sstack_ld(saddr, sp, ref, tb);
+    return ref;
+}
+
 }  // namespace prt

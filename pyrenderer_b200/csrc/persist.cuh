@@ -122,7 +122,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                 if (COUNT) ++c_nodes;
                 NodeHits h;
                 node_test4<false>(sc.nodes + cur, rb, tmin, bound, h);
-                cur = descend(h, saddr, ovf, sp, bound);
+                cur = MODE == MODE_ANY ? descend_any(h, saddr, ovf, sp) : descend(h, saddr, ovf, sp, bound);
             }
         }
 
