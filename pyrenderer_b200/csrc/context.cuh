@@ -47,7 +47,7 @@ struct prt_ctx {
     void* stage[2] = {nullptr, nullptr};
     size_t stage_bytes[2] = {0, 0};
     static constexpr int kHostSlots = 4;  // chunks in flight in prt_trace_closest_host
-    cudaStream_t copy_stream[3] = {nullptr, nullptr, nullptr};  // upload, compute, download
+    cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // upload, trace A, download, trace B
     cudaEvent_t copy_event[3 * kHostSlots] = {};                // per slot: uploaded, traced, downloaded
 
     // wavefront state (wavefront.cu)

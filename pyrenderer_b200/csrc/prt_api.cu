@@ -258,9 +258,11 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
     USE_DEVICE(ctx);
     if (n == 0) return PRT_OK;
     if (!rays_host || !hits_host) { ctx->set_error("trace_host: NULL buffer"); return PRT_ERR_INVALID; }
-    // Three streams (upload, trace, download) and kHostSlots staging slots: the upload of chunk
-    // i+1.., the trace of chunk i and the download of chunk i-1 overlap; traces never overlap each
-    // other (a persistent launch fills the GPU) and each copy engine sees a FIFO.
+    // Upload, download and two alternating trace streams over kHostSlots staging slots: the upload
+    // of chunk i+1.., the trace of chunk i and the download of chunk i-1 overlap, each copy engine
+    // sees a FIFO, and because consecutive traces sit on different streams the CTAs of chunk i+1
+    // move into the SM slots that the draining tail of chunk i frees (a persistent launch ends with
+    // a few long rays on mostly idle SMs).  EXACT launches share one flag list: one trace stream.
     constexpr int S = prt_ctx::kHostSlots;
     const uint64_t chunk = 1ull << 21;
     const uint64_t cap = n < S * chunk ? n : S * chunk;
@@ -273,10 +275,12 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
         if (!ev) PRT_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     prt_ray* dr = (prt_ray*)ctx->stage[0];
     prt_hit* dh = (prt_hit*)ctx->stage[1];
-    cudaStream_t s_up = ctx->copy_stream[0], s_tr = ctx->copy_stream[1], s_down = ctx->copy_stream[2];
+    cudaStream_t s_up = ctx->copy_stream[0], s_down = ctx->copy_stream[2];
+    const bool one_trace_stream = (flags & PRT_TRACE_EXACT) != 0;
     uint64_t done = 0;
     for (uint64_t i = 0; done < n; ++i) {
         const int slot = (int)(i % S);
+        cudaStream_t s_tr = ctx->copy_stream[(one_trace_stream || (i & 1) == 0) ? 1 : 3];
         cudaEvent_t uploaded = ctx->copy_event[3 * slot], traced = ctx->copy_event[3 * slot + 1],
                     downloaded = ctx->copy_event[3 * slot + 2];
         const uint64_t m = n - done < chunk ? n - done : chunk;
@@ -294,10 +298,14 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
         PRT_CUDA_TRY(ctx, cudaEventRecord(downloaded, s_down));
         done += m;
     }
-    cudaError_t e0 = cudaStreamSynchronize(s_up), e1 = cudaStreamSynchronize(s_tr), e2 = cudaStreamSynchronize(s_down);
+    cudaError_t err = cudaSuccess;
+    for (auto& st : ctx->copy_stream) {
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (err == cudaSuccess) err = e;
+    }
     if (rc != PRT_OK) return rc;
-    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
-        ctx->set_error("trace_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+    if (err != cudaSuccess) {
+        ctx->set_error("trace_host: %s", cudaGetErrorString(err));
         return PRT_ERR_CUDA;
     }
     return PRT_OK;
