@@ -230,8 +230,11 @@ __device__ __forceinline__ float tri_area_gid(const SceneDev& sc, uint32_t gid) 
 // sampling are weighted with the power heuristic (the scheme of the reference's draft
 // sample_direct_lighting2, core/tracing.py:56-90), the path ends on an emitter.  beta.w carries
 // the solid-angle pdf of the BSDF sample that produced the current ray (< 0: camera / specular).
+#ifndef PRT_SHADE_MIN_BLOCKS
+#define PRT_SHADE_MIN_BLOCKS 4
+#endif
 template <bool PHYS, bool LOG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PRT_SHADE_MIN_BLOCKS)
 shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, float4* rays,
              const float4* __restrict__ hits, float4* beta, float4* L, float4* srays,
              float4* scontrib, const uint32_t* __restrict__ queue_in, uint32_t* queue_out,
