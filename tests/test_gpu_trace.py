@@ -389,3 +389,32 @@ def test_million_triangle_soup_bvh_equals_exhaustive(gpu_ctx):
     gpu_closest(gpu_ctx, rays, COUNT)
     c = gpu_ctx.counters()
     print(f"[soup1M] mean node visits {c['node_visits'] / rays.shape[0]:.1f} tri tests {c['tri_tests'] / rays.shape[0]:.1f}")
+
+
+def test_fuzz_small_scenes_exact_ids(gpu_ctx):
+    """Many small random scenes through the whole builder (Morton sort, Karras, SAH treelets,
+    refit + rotations, 4-wide emit) and the exact closest-hit path: sizes around every builder
+    boundary (1, 2, treelet size 128, its multiples), duplicated triangles, degenerate (zero-area)
+    triangles and widely different scales in one scene."""
+    rng = np.random.default_rng(2024)
+    sizes = [1, 2, 3, 7, 31, 100, 128, 129, 255, 256, 257, 300, 511, 640, 1000]
+    for i, nt in enumerate(sizes):
+        kind = i % 3
+        if kind == 0:
+            tris = random_soup(nt, seed=500 + nt)
+        elif kind == 1:  # duplicates + degenerate triangles
+            base = random_soup(max(1, nt // 2), seed=600 + nt)
+            tris = base[np.arange(nt) % base.shape[0]].copy()
+            tris[::5, 2] = tris[::5, 1]  # zero-area
+        else:  # mixed scales: a few huge triangles over many tiny ones
+            tris = random_soup(nt, seed=700 + nt)
+            big = rng.integers(0, nt, max(1, nt // 20))
+            tris[big] = (rng.uniform(-3, 4, (big.size, 3, 3))).astype(np.float32)
+        rays = random_rays(1500, seed=nt)
+        gpu_ctx.set_triangles(tris)
+        st = gpu_ctx.build_bvh(max_leaf_tris=(1, 4, 7)[i % 3])
+        assert st["n_tris"] == nt and st["morton_sorted"] == 1
+        check_against_oracle(gpu_ctx, tris, rays, EXACT, f"fuzz{nt}/{kind}")
+        ids_o = oracle.closest_hit(tris, rays)[0]
+        ids_f = gpu_closest(gpu_ctx, rays, 0)[0]
+        assert np.mean(ids_f != ids_o) < 5e-3, f"fuzz{nt}/{kind}: plain FP32 mismatch {np.mean(ids_f != ids_o):.2e}"
