@@ -354,10 +354,18 @@ def main():
             acc_o = oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"], ocam,
                                   oracle.make_params(**kw))[0]
             c1_cpu_ms = (time.perf_counter() - t0) * 1e3
+            all_threads = oracle.num_threads()
+            t0 = time.perf_counter()  # the reference's literal setting: joblib n_jobs=4 (main.py:52)
+            oracle.render(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"], ocam,
+                          oracle.make_params(**kw), nthreads=4)
+            c1_cpu4_ms = (time.perf_counter() - t0) * 1e3
+            # omp_set_num_threads is sticky: hand all threads back before the soup baseline below
+            oracle.closest_hit(a["tris"][:1], np.zeros((1, 8), np.float32), nthreads=all_threads)
             g = acc1.cpu().numpy().astype(np.float64)[..., :3]
             c1 = {"workload": "cornell-box 256x256, 16 spp, max depth 5 (BASELINE configs[0])",
                   "gpu_ms": c1_gpu_ms, "gpu_spp_per_s": 16 / (c1_gpu_ms * 1e-3),
-                  "cpu_port_ms": c1_cpu_ms, "cpu_port_spp_per_s": 16 / (c1_cpu_ms * 1e-3), "cpu_cores": oracle.num_threads(),
+                  "cpu_port_ms": c1_cpu_ms, "cpu_port_spp_per_s": 16 / (c1_cpu_ms * 1e-3), "cpu_cores": all_threads,
+                  "cpu_port_4_threads_ms": c1_cpu4_ms,
                   "rel_rmse_gpu_vs_oracle_equal_seed": float(np.sqrt(np.mean((g - acc_o[..., :3]) ** 2)) / np.mean(acc_o[..., :3]))}
             render["c1"] = c1
         rctx.close()
