@@ -84,6 +84,8 @@ typedef struct {
     double sensor_h; /* tan(radians(fov)/2) * focal */
     double focal;
     uint32_t width, height;
+    double aperture; /* core/camera.py:63-65: side of the square lens the ray origin is drawn from
+                        (camera space x,y in [-aperture/2, aperture/2)); 0 = pinhole (the loader's value) */
 } prt_camera;
 
 typedef struct {

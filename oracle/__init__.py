@@ -23,7 +23,8 @@ assert MATERIAL_DTYPE.itemsize == 48
 
 class Camera(C.Structure):
     _fields_ = [("iview", C.c_double * 16), ("sensor_w", C.c_double), ("sensor_h", C.c_double),
-                ("focal", C.c_double), ("width", C.c_uint32), ("height", C.c_uint32)]
+                ("focal", C.c_double), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("aperture", C.c_double)]
 
 
 class RenderParams(C.Structure):
@@ -156,13 +157,14 @@ def cosine_sample_hemisphere(n, u1, u2):
     return out
 
 
-def make_camera(iview, sensor_w, sensor_h, focal, width, height):
+def make_camera(iview, sensor_w, sensor_h, focal, width, height, aperture=0.0):
     cam = Camera()
     iv = np.ascontiguousarray(iview, dtype=np.float64).reshape(16)
     for i in range(16):
         cam.iview[i] = float(iv[i])
     cam.sensor_w, cam.sensor_h, cam.focal = float(sensor_w), float(sensor_h), float(focal)
     cam.width, cam.height = int(width), int(height)
+    cam.aperture = float(aperture)
     return cam
 
 

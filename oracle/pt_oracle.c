@@ -69,6 +69,7 @@ typedef struct {
     double sensor_h;
     double focal;
     uint32_t width, height;
+    double aperture; /* camera.py:63-65; 0 = pinhole */
 } orc_camera;
 
 typedef struct {
@@ -398,21 +399,32 @@ void orc_cosine_sample_hemisphere(const double n[3], double u1, double u2, doubl
 }
 
 /* ---- camera (core/camera.py:41-72) ------------------------------------- */
-void orc_generate_ray(const orc_camera* cam, double u, double v, double o_out[3], double d_out[3]) {
+/* (lu, lv) in [0,1)^2: the two random() draws of camera.py:64-65 (only read when aperture > 0) */
+void orc_generate_ray_lens(const orc_camera* cam, double u, double v, double lu, double lv, double o_out[3],
+                           double d_out[3]) {
     double cs0 = u - 0.5, cs1 = v - 0.5;
     double rd[3] = {cs0 * cam->sensor_w / 0.5, cs1 * cam->sensor_h / 0.5, -cam->focal};
     /* to_homogeneous_vector rounds to float32 (vec3.py:20-23) */
     double h[4] = {(double)(float)rd[0], (double)(float)rd[1], (double)(float)rd[2], 1.0};
     const double* m = cam->iview;
     double dw[4], ow[4];
+    double ax = 0.0, ay = 0.0;
+    if (cam->aperture > 0.0) { /* camera.py:63-65, then to_homogeneous_vector's f32 rounding */
+        ax = (double)(float)(cam->aperture * lu - cam->aperture / 2.0);
+        ay = (double)(float)(cam->aperture * lv - cam->aperture / 2.0);
+    }
     for (int j = 0; j < 4; ++j) {
         dw[j] = ((h[0] * m[0 * 4 + j] + h[1] * m[1 * 4 + j]) + h[2] * m[2 * 4 + j]) + h[3] * m[3 * 4 + j];
-        ow[j] = ((0.0 * m[0 * 4 + j] + 0.0 * m[1 * 4 + j]) + 0.0 * m[2 * 4 + j]) + 1.0 * m[3 * 4 + j];
+        ow[j] = cam->aperture > 0.0 ? (ax * m[0 * 4 + j] + ay * m[1 * 4 + j]) + 1.0 * m[3 * 4 + j]
+                                    : ((0.0 * m[0 * 4 + j] + 0.0 * m[1 * 4 + j]) + 0.0 * m[2 * 4 + j]) + 1.0 * m[3 * 4 + j];
     }
     double f[3] = {dw[0] - ow[0], dw[1] - ow[1], dw[2] - ow[2]};
     normalize3(f);
     o_out[0] = ow[0]; o_out[1] = ow[1]; o_out[2] = ow[2];
     d_out[0] = f[0]; d_out[1] = f[1]; d_out[2] = f[2];
+}
+void orc_generate_ray(const orc_camera* cam, double u, double v, double o_out[3], double d_out[3]) {
+    orc_generate_ray_lens(cam, u, v, 0.5, 0.5, o_out, d_out); /* lens centre: offset exactly 0 */
 }
 
 /* Primary rays for pixel (i,j) samples [s0,s1): main.py:31-33.  Output in the
@@ -424,15 +436,15 @@ int orc_generate_rays(const orc_camera* cam, uint64_t seed, uint32_t s0, uint32_
     for (int64_t p = 0; p < (int64_t)W * H; ++p) {
         uint32_t i = (uint32_t)(p % W), j = (uint32_t)(p / W);
         for (uint32_t s = s0; s < s1; ++s) {
-            double jx = 0.5, jy = 0.5;
+            double jx = 0.5, jy = 0.5, lu = 0.5, lv = 0.5;
             if (jitter) {
                 uint32_t r[4];
                 rng4(seed, (uint32_t)p, s, 0, 0, r);
-                jx = u24(r[0]); jy = u24(r[1]);
+                jx = u24(r[0]); jy = u24(r[1]); lu = u24(r[2]); lv = u24(r[3]);
             }
             double u = ((double)i + jx) / (double)W, v = ((double)j + jy) / (double)H;
             double o[3], d[3];
-            orc_generate_ray(cam, u, v, o, d);
+            orc_generate_ray_lens(cam, u, v, lu, lv, o, d);
             float* out = rays + ((size_t)p * ns + (s - s0)) * 8;
             out[0] = (float)o[0]; out[1] = (float)o[1]; out[2] = (float)o[2]; out[3] = tmin;
             out[4] = (float)d[0]; out[5] = (float)d[1]; out[6] = (float)d[2]; out[7] = tmax;
@@ -760,7 +772,7 @@ int orc_render(const float* tris, const float* normals, uint32_t nt, const uint3
             double u = ((double)i + u24(r[0])) / (double)W;
             double v = ((double)j + u24(r[1])) / (double)H;
             double o[3], d[3], L[3];
-            orc_generate_ray(cam, u, v, o, d);
+            orc_generate_ray_lens(cam, u, v, u24(r[2]), u24(r[3]), o, d);
             /* rays cross the device boundary as f32 records */
             for (int k = 0; k < 3; ++k) { o[k] = (double)(float)o[k]; d[k] = (double)(float)d[k]; }
             int32_t pid;

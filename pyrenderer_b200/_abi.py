@@ -27,7 +27,8 @@ RENDER_PHYSICAL = 2
 
 class PrtCamera(C.Structure):
     _fields_ = [("iview", C.c_double * 16), ("sensor_w", C.c_double), ("sensor_h", C.c_double),
-                ("focal", C.c_double), ("width", C.c_uint32), ("height", C.c_uint32)]
+                ("focal", C.c_double), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("aperture", C.c_double)]
 
 
 class PrtRenderParams(C.Structure):
@@ -185,13 +186,14 @@ class Context:
         self._check(self.lib.prt_bvh_build(self.h, C.byref(opts), C.byref(st)))
         return {k: getattr(st, k) for k, _ in PrtBvhStats._fields_}
 
-    def set_camera(self, iview, sensor_w, sensor_h, focal, width, height):
+    def set_camera(self, iview, sensor_w, sensor_h, focal, width, height, aperture=0.0):
         cam = PrtCamera()
         iv = np.ascontiguousarray(iview, np.float64).reshape(16)
         for i in range(16):
             cam.iview[i] = float(iv[i])
         cam.sensor_w, cam.sensor_h, cam.focal = float(sensor_w), float(sensor_h), float(focal)
         cam.width, cam.height = int(width), int(height)
+        cam.aperture = float(aperture)
         self._check(self.lib.prt_camera_set(self.h, C.byref(cam)))
         self.resolution = (int(width), int(height))
 

@@ -8,6 +8,8 @@ with the same operation order, so both produce the same f32 ray records.
 """
 from math import radians, tan
 
+from random import random
+
 import numpy as np
 
 from .ray import Ray
@@ -65,6 +67,13 @@ class Camera:
         m = self.iview
         d_w = ((h[0] * m[0] + h[1] * m[1]) + h[2] * m[2]) + h[3] * m[3]
         o_w = m[3].copy()
+        if self.aperture > 0:  # thin lens: origin on a square lens in camera space (camera.py:63-65)
+            o_cam = np.zeros(4, np.float32)
+            o_cam[0] = self.aperture * random() - self.aperture / 2.0
+            o_cam[1] = self.aperture * random() - self.aperture / 2.0
+            o_cam[3] = 1.0
+            g = o_cam.astype(np.float64)
+            o_w = (g[0] * m[0] + g[1] * m[1]) + g[3] * m[3]
         d = (d_w - o_w)[:3]
         d = d / np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
         return Ray(o_w[:3], d, 8)

@@ -40,7 +40,7 @@ def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_O
     """
     torch = _torch()
     ctx = scene.commit(device)
-    ctx.set_camera(*camera.device_record())
+    ctx.set_camera(*camera.device_record(), aperture=float(getattr(camera, "aperture", 0.0)))
     if accum is None:
         accum = new_accum(camera, device)
     w, h = camera.get_resolution()

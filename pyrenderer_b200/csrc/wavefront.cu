@@ -46,7 +46,7 @@ struct WaveState {
 
 struct CamDev {
     double m[16];
-    double sw, sh, focal;
+    double sw, sh, focal, aperture;
     uint32_t W, H;
 };
 
@@ -75,7 +75,8 @@ __device__ __forceinline__ void log_segment(const WaveParams& P, float3 p0, floa
     }
 }
 
-__device__ __forceinline__ void camera_ray(const CamDev& cam, double u, double v, float4& ro,
+// (lu, lv): lens sample in [0,1)^2, used only when cam.aperture > 0 (core/camera.py:63-65)
+__device__ __forceinline__ void camera_ray(const CamDev& cam, double u, double v, double lu, double lv, float4& ro,
                                            float4& rd, float tmin, float tmax) {
     // core/camera.py:48-70 in the oracle's operation order (oracle/pt_oracle.c orc_generate_ray)
     double cs0 = __dsub_rn(u, 0.5), cs1 = __dsub_rn(v, 0.5);
@@ -88,6 +89,11 @@ __device__ __forceinline__ void camera_ray(const CamDev& cam, double u, double v
         double dw = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h0, cam.m[j]), __dmul_rn(h1, cam.m[4 + j])),
                                         __dmul_rn(h2, cam.m[8 + j])), cam.m[12 + j]);
         o[j] = cam.m[12 + j];
+        if (cam.aperture > 0.0) {  // origin (ax, ay, 0, 1) @ iview, f32-rounded like every homogeneous vector (vec3.py:20-23)
+            const double ax = (double)__double2float_rn(__dsub_rn(__dmul_rn(cam.aperture, lu), __ddiv_rn(cam.aperture, 2.0)));
+            const double ay = (double)__double2float_rn(__dsub_rn(__dmul_rn(cam.aperture, lv), __ddiv_rn(cam.aperture, 2.0)));
+            o[j] = __dadd_rn(__dadd_rn(__dmul_rn(ax, cam.m[j]), __dmul_rn(ay, cam.m[4 + j])), cam.m[12 + j]);
+        }
         f[j] = __dsub_rn(dw, o[j]);
     }
     double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(f[0], f[0]), __dmul_rn(f[1], f[1])), __dmul_rn(f[2], f[2])));
@@ -104,15 +110,16 @@ __global__ void generate_rays_kernel(CamDev cam, unsigned long long seed, uint32
     if (idx >= total) return;
     uint32_t pixel = (uint32_t)(idx / ns), s = s0 + (uint32_t)(idx % ns);
     uint32_t i = pixel % cam.W, j = pixel / cam.W;
-    double jx = 0.5, jy = 0.5;
+    double jx = 0.5, jy = 0.5, lu = 0.5, lv = 0.5;
     if (jitter) {
         uint4 r = rng4(seed, pixel, s, 0, 0);
         jx = (double)u24(r.x); jy = (double)u24(r.y);
+        lu = (double)u24(r.z); lv = (double)u24(r.w);
     }
     double u = __ddiv_rn(__dadd_rn((double)i, jx), (double)cam.W);
     double v = __ddiv_rn(__dadd_rn((double)j, jy), (double)cam.H);
     float4 ro, rd;
-    camera_ray(cam, u, v, ro, rd, tmin, tmax);
+    camera_ray(cam, u, v, lu, lv, ro, rd, tmin, tmax);
     rays[2 * idx] = ro;
     rays[2 * idx + 1] = rd;
 }
@@ -129,7 +136,7 @@ __global__ void raygen_kernel(CamDev cam, WaveParams P, float4* rays, float4* be
     double u = __ddiv_rn(__dadd_rn((double)i, (double)u24(r.x)), (double)cam.W);
     double v = __ddiv_rn(__dadd_rn((double)j, (double)u24(r.y)), (double)cam.H);
     float4 ro, rd;
-    camera_ray(cam, u, v, ro, rd, P.tmin, P.tmax);
+    camera_ray(cam, u, v, (double)u24(r.z), (double)u24(r.w), ro, rd, P.tmin, P.tmax);
     rays[2 * (size_t)pid] = ro;
     rays[2 * (size_t)pid + 1] = rd;
     beta[pid] = make_float4(1.f, 1.f, 1.f, -1.f);
@@ -452,7 +459,7 @@ __global__ void accumulate_kernel(const float4* __restrict__ L, uint32_t npix, u
 static CamDev cam_dev(const prt_camera& c) {
     CamDev d;
     for (int i = 0; i < 16; ++i) d.m[i] = c.iview[i];
-    d.sw = c.sensor_w; d.sh = c.sensor_h; d.focal = c.focal;
+    d.sw = c.sensor_w; d.sh = c.sensor_h; d.focal = c.focal; d.aperture = c.aperture;
     d.W = c.width; d.H = c.height;
     return d;
 }

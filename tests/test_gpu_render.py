@@ -300,3 +300,31 @@ def test_path_log_segments_form_paths(cornell):
     # logging is off again: a second call leaves a fresh logger empty-handed only if asked without one
     e2, r2 = tracing.path_tracing(rays, scene, None, spp=2, max_depth=4, seed=5)
     assert np.array_equal(e, e2) and np.array_equal(r, r2)
+
+
+def test_thin_lens_device_matches_oracle(gpu_ctx, cornell):
+    """aperture > 0 (core/camera.py:63-65): device raygen == oracle raygen bit for bit (lens sample =
+    words 2,3 of Philox block 0), and a depth-of-field render matches the oracle at equal seed."""
+    torch = _torch()
+    scene, cam = cornell
+    a = scene.arrays()
+    W, H = 320, 256  # large enough for the 1e-3 tolerance: one divergent FP32/f64 path weighs 1/sqrt(pixels)
+    gpu_ctx.set_triangles(a["tris"], a["normals"], a["tri_material"], a["materials"], a["light_tris"])
+    gpu_ctx.build_bvh()
+    iview, sw, sh, focal, _, _ = cam.device_record()
+    sw = sh * W / H
+    gpu_ctx.set_camera(iview, sw, sh, focal, W, H, aperture=0.3)
+    ocam = oracle.make_camera(iview, sw, sh, focal, W, H, aperture=0.3)
+    rays = torch.empty((H * W * 3, 8), dtype=torch.float32, device="cuda")
+    gpu_ctx.generate_rays(rays, seed=7, s0=2, s1=5, jitter=True)
+    torch.cuda.synchronize()
+    rays_o = oracle.generate_rays(ocam, seed=7, s0=2, s1=5, jitter=True).reshape(-1, 8)
+    assert np.array_equal(rays.cpu().numpy().view(np.uint32), rays_o.view(np.uint32))
+    assert np.unique(rays_o[:, 0]).size > 10000  # the origins really move over the lens
+    kw = dict(seed=3, spp_begin=0, spp_end=16, max_depth=4)
+    acc_g, _ = gpu_render(gpu_ctx, W, H, **kw)
+    acc_o, _, _ = oracle_render(a, ocam, **kw)
+    err = rel_rmse(acc_g[..., :3], acc_o[..., :3])
+    print(f"[thin lens] rel RMSE {err:.3e}")
+    assert err < 1e-3
+    gpu_ctx.set_camera(iview, sw, sh, focal, W, H)  # leave the shared context a pinhole again

@@ -143,7 +143,7 @@ def test_abi_fails_loudly_without_gpu():
 def test_struct_layouts_match_oracle():
     from pyrenderer_b200 import _abi
     assert _abi.MATERIAL_DTYPE == oracle.MATERIAL_DTYPE
-    assert ctypes.sizeof(_abi.PrtCamera) == ctypes.sizeof(oracle.Camera) == 160
+    assert ctypes.sizeof(_abi.PrtCamera) == ctypes.sizeof(oracle.Camera) == 168
     assert ctypes.sizeof(_abi.PrtRenderParams) == ctypes.sizeof(oracle.RenderParams) == 48
     assert _abi.HIT_DTYPE.itemsize == 16
 
@@ -281,3 +281,36 @@ def test_hdr_output_roundtrip(tmp_path):
     assert np.array_equal(read_pfm(p), img)
     head = open(p, "rb").read(12)
     assert head.startswith(b"PF\n5 7\n")
+
+
+def test_thin_lens_camera_host_and_oracle(cornell):
+    """core/camera.py:63-65: with aperture > 0 the ray starts on a square lens (camera-space x, y in
+    [-a/2, a/2)) and still aims at the pinhole ray's point on the plane z = -focal_dist: all lens rays
+    of one screen coordinate meet there.  aperture == 0 (the loader's value) stays bit-identical."""
+    import oracle
+    from pyrenderer_b200.core.camera import Camera
+    pin = Camera([0, 1, 6.8], [0, 1, 0], [0, 1, 0], [64, 64], fov=19.5, focal_dist=6.0)
+    lens = Camera([0, 1, 6.8], [0, 1, 0], [0, 1, 0], [64, 64], fov=19.5, aperture=0.4, focal_dist=6.0)
+    uv = np.array([0.3, 0.8])
+    r0 = pin.generate_ray(uv)
+    focus = r0.position + r0.direction * (6.0 / -r0.direction[2])  # plane z_cam = -6  <=>  world z = 0.8
+    origins = []
+    for _ in range(50):
+        r = lens.generate_ray(uv)
+        t = (focus[2] - r.position[2]) / r.direction[2]
+        assert np.allclose(r.position + t * r.direction, focus, atol=1e-6)
+        assert abs(np.linalg.norm(r.direction) - 1) < 1e-12 and abs(r.position[2] - 6.8) < 1e-12
+        origins.append(r.position[:2] - np.array([0.0, 1.0]))
+    origins = np.array(origins)
+    assert np.all(np.abs(origins) <= 0.2 + 1e-7) and origins.std(axis=0).min() > 0.05
+    # oracle: same construction with explicit lens samples; lens centre == pinhole, bit for bit
+    iview, sw, sh, focal, W, H = lens.device_record()
+    oc_pin = oracle.make_camera(iview, sw, sh, focal, W, H)
+    oc_lens = oracle.make_camera(iview, sw, sh, focal, W, H, aperture=0.4)
+    o0, d0 = oracle.generate_ray(oc_pin, 0.3, 0.8)
+    assert np.array_equal(o0, r0.position) and np.allclose(d0, r0.direction, atol=1e-15)
+    rays = oracle.generate_rays(oc_lens, seed=4, s0=0, s1=8, jitter=True)
+    o = rays[..., 0:3].reshape(-1, 3).astype(np.float64) - np.array([0.0, 1.0, 6.8])
+    assert np.abs(o[:, 2]).max() < 1e-6 and np.abs(o[:, :2]).max() <= 0.2 + 1e-6 and o[:, :2].std(axis=0).min() > 0.08
+    rays0 = oracle.generate_rays(oc_pin, seed=4, s0=0, s1=8, jitter=True)
+    assert np.all(rays0[..., 0:3] == np.array([0.0, 1.0, 6.8], np.float32))
