@@ -328,3 +328,35 @@ def test_thin_lens_device_matches_oracle(gpu_ctx, cornell):
     print(f"[thin lens] rel RMSE {err:.3e}")
     assert err < 1e-3
     gpu_ctx.set_camera(iview, sw, sh, focal, W, H)  # leave the shared context a pinhole again
+
+
+def test_world_container_of_the_taichi_path(cornell):
+    """main_taichi.py:41-44: World().add(p) ... commit(); PathTracer(world, depth, w, h); hit_all's
+    8-tuple agrees with Scene.hit and the cosine pdf."""
+    from pyrenderer_b200.core import tracing
+    from pyrenderer_b200.core.ray import Ray
+    from pyrenderer_b200.mathematics.intersection_taichi import World
+    scene, cam = cornell
+    empty = World()
+    with pytest.raises(AssertionError):
+        empty.commit()
+    world = World(seed=1)
+    for p in scene.primitives:
+        world.add(p)
+    world.commit()
+    eye = np.array([0.0, 1.0, 6.8])
+    d = np.array([0.5, 0.0, 0.5]) - eye
+    d /= np.linalg.norm(d)
+    hit, t, p, normal, emissive, att, wi, pdf = world.hit_all(eye, d, 1e-5, 99999.9)
+    ref = scene.hit(Ray(eye, d))
+    assert hit and abs(t - ref["t"]) < 1e-12 and np.allclose(normal, ref["normal"]) and emissive == 0
+    assert np.allclose(p, eye + t * d) and np.allclose(p, ref["position"]) and np.allclose(att, [0.725, 0.71, 0.68])
+    assert abs(np.linalg.norm(wi) - 1) < 1e-12 and np.dot(wi, normal) > 0 and abs(pdf - np.dot(wi, normal) / np.pi) < 1e-12
+    to_light = np.array([-0.005, 1.98, -0.03]) - eye
+    many = world.hit_all(np.tile(eye, (3, 1)), np.array([d, to_light / np.linalg.norm(to_light), [0.0, 0.0, 1.0]]))
+    assert list(many[0]) == [True, True, False] and list(many[4]) == [0, 1, 0]
+    point, n2, em = world.sample_a_light()
+    assert abs(point[1] - 1.98) < 1e-6 and np.allclose(n2, [0, -1, 0], atol=1e-6) and np.allclose(em, 1.0)
+    acc = tracing.PathTracer(world, 4, 32, 32).trace_image(cam, spp=2, seed=3)
+    acc2 = tracing.render(scene, cam, spp=2, max_depth=4, seed=3)
+    assert np.array_equal(acc.cpu().numpy(), acc2.cpu().numpy())
