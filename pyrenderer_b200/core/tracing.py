@@ -161,6 +161,19 @@ class PathTracer:
         self.depth = depth
         self.img_w, self.img_h = img_w, img_h
 
+    def trace(self, ro, rd, depth=None, x=0, y=0, spp=1, seed=1):
+        """Radiance along one ray (or [n,3] arrays of rays): the host form of the reference's
+        ``@ti.func trace(ro, rd, depth, x, y)`` (core/tracing.py:116-155).  (x, y) only seed the
+        Philox stream there is no per-pixel state to index."""
+        from .ray import Ray
+        o = np.atleast_2d(np.asarray(ro, np.float64))
+        d = np.atleast_2d(np.asarray(rd, np.float64))
+        rays = [Ray(o[i], d[i]) for i in range(o.shape[0])]
+        e, r = path_tracing(rays, self.world, spp=spp, max_depth=self.depth if depth is None else depth,
+                            seed=seed + 7919 * int(x) + 104729 * int(y))
+        out = e + r
+        return out[0] if np.asarray(ro).ndim == 1 else out
+
     def trace_image(self, camera, spp=1, seed=1, spp_begin=0, accum=None, device=0):
         return render(self.world, camera, spp=spp, max_depth=self.depth, seed=seed,
                       spp_begin=spp_begin, accum=accum, device=device)

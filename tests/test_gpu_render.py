@@ -357,6 +357,9 @@ def test_world_container_of_the_taichi_path(cornell):
     assert list(many[0]) == [True, True, False] and list(many[4]) == [0, 1, 0]
     point, n2, em = world.sample_a_light()
     assert abs(point[1] - 1.98) < 1e-6 and np.allclose(n2, [0, -1, 0], atol=1e-6) and np.allclose(em, 1.0)
-    acc = tracing.PathTracer(world, 4, 32, 32).trace_image(cam, spp=2, seed=3)
+    pt = tracing.PathTracer(world, 4, 32, 32)
+    l_o = pt.trace(eye, to_light / np.linalg.norm(to_light), 4, 10, 20)
+    assert np.allclose(l_o, [0.9, 0.85, 0.7], atol=1e-6)  # core/tracing.py:120,134: light seen directly
+    acc = pt.trace_image(cam, spp=2, seed=3)
     acc2 = tracing.render(scene, cam, spp=2, max_depth=4, seed=3)
     assert np.array_equal(acc.cpu().numpy(), acc2.cpu().numpy())
