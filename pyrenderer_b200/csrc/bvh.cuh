@@ -49,11 +49,7 @@ __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
 __device__ __forceinline__ RayBox make_raybox_fast(float3 o, float3 d) {  // persist.cuh: see rcp_fast
     RayBox r;
     r.o = o;
-#ifdef PRT_SLOW_RCP
-    r.idir = make_float3(__fdiv_rn(1.0f, clamp_dir(d.x)), __fdiv_rn(1.0f, clamp_dir(d.y)), __fdiv_rn(1.0f, clamp_dir(d.z)));
-#else
     r.idir = make_float3(rcp_fast(clamp_dir(d.x)), rcp_fast(clamp_dir(d.y)), rcp_fast(clamp_dir(d.z)));
-#endif
     r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
     return r;
 }
@@ -69,21 +65,10 @@ __device__ __forceinline__ float qf(uint32_t w, int byte) {
 #ifndef PRT_LDG256
 #define PRT_LDG256 1
 #endif
-#ifndef PRT_L2_HINT
-#define PRT_L2_HINT 0  // 1: BVH loads carry an L2 evict_last policy (rays / hits stream through evict-first)
-#endif
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
-#if PRT_L2_HINT
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-                 : "l"(p), "l"(pol));
-#else
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p));
-#endif
 }
 // streaming (evict-first) 256-bit load of one 32-byte ray record: one sector, one request
 __device__ __forceinline__ void ldg256_cs(const void* p, float4& a, float4& b) {
@@ -209,9 +194,7 @@ __device__ __forceinline__ void node_test4(const Node64* __restrict__ node, cons
 // lets a pop discard, without touching memory, every subtree that a closer hit found in the
 // meantime has made irrelevant.
 constexpr int kSpill = kPStack / 2;
-#ifndef PRT_SPILL_INL
-#define PRT_SPILL_INL __forceinline__  // a real call costs 4 % (ABI constraints on the hot loop)
-#endif
+// (inlined: as real calls the two slow paths cost 4 % -- ABI constraints on the hot loop)
 constexpr uint32_t kStackStride = kTraceThreads * 8u;
 __device__ __forceinline__ void sstack_st(uint32_t saddr, int i, uint32_t ref, uint32_t tb) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr + (uint32_t)i * kStackStride), "r"(ref), "r"(tb) : "memory");
@@ -221,7 +204,7 @@ __device__ __forceinline__ void sstack_ld(uint32_t saddr, int i, uint32_t& ref, 
 }
 __device__ __forceinline__ void sstack_reset(uint2* ovf, int& sp) { sp = 0; ovf[0].x = 0u; }
 // (sp by value in and out: a reference parameter of a real call would pin sp to local memory)
-static __device__ PRT_SPILL_INL int sstack_spill(uint32_t saddr, uint2* ovf, int sp) {
+static __device__ __forceinline__ int sstack_spill(uint32_t saddr, uint2* ovf, int sp) {
     const uint32_t n = ovf[0].x;
     for (int i = 0; i < kSpill; ++i) {
         uint32_t r, t;
@@ -236,7 +219,7 @@ static __device__ PRT_SPILL_INL int sstack_spill(uint32_t saddr, uint2* ovf, int
     ovf[0].x = n + kSpill;
     return sp - kSpill;
 }
-static __device__ PRT_SPILL_INL int sstack_unspill(uint32_t saddr, uint2* ovf) {  // shared part empty; returns the new sp
+static __device__ __forceinline__ int sstack_unspill(uint32_t saddr, uint2* ovf) {  // shared part empty; returns the new sp
     const uint32_t n = ovf[0].x;
     if (n == 0u) return 0;
     for (int i = 0; i < kSpill; ++i) {
@@ -276,9 +259,7 @@ __device__ __forceinline__ void sort_hits(NodeHits& h) {
     cswap(h.t[2], h.ref[2], h.t[3], h.ref[3]);
     cswap(h.t[0], h.ref[0], h.t[2], h.ref[2]);
     cswap(h.t[1], h.ref[1], h.t[3], h.ref[3]);
-#if !defined(PRT_SORT4)
-    cswap(h.t[1], h.ref[1], h.t[2], h.ref[2]);
-#endif
+    cswap(h.t[1], h.ref[1], h.t[2], h.ref[2]);  // (dropping this comparator costs 5 % more visits)
 }
 
 // push the (sorted) hits 3, 2, 1: three unconditional stores, the stack pointer advances only

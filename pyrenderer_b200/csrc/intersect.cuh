@@ -139,13 +139,9 @@ __device__ __forceinline__ RayWF make_raywf(float3 o, float3 d) {
         const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
         r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
         const float3 p = perm3(d, r.kz);
-#ifdef PRT_SLOW_RCP
-        r.Sx = __fdiv_rn(p.x, p.z); r.Sy = __fdiv_rn(p.y, p.z); r.Sz = __fdiv_rn(1.0f, p.z);
-#else
         r.Sz = rcp_fast(p.z);
         r.Sx = p.x * r.Sz;
         r.Sy = p.y * r.Sz;
-#endif
     }
     RayWF f;
     f.o = o;
