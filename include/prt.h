@@ -18,7 +18,9 @@
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *    Calls are stream-ordered and asynchronous unless stated otherwise.
  *  - one context per device; a context is not thread-safe, distinct contexts
- *    are independent.
+ *    are independent (prt_last_error(NULL), the text of a failed prt_create, is
+ *    kept per calling thread).  Every call makes the context's device current
+ *    for its duration and restores the caller's current device on return.
  *  - there is no CPU fallback: without a CUDA device prt_create fails.
  */
 #ifndef PRT_H
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PRT_ABI_VERSION 2
+#define PRT_ABI_VERSION 3
 
 typedef struct prt_ctx prt_ctx;
 
@@ -125,11 +127,18 @@ typedef struct {
      * loop iterations per warp, lanes doing a record visit summed over iterations, leaf
      * phases and lanes intersecting in them */
     uint64_t warp_iters, node_lane_iters, leaf_phases, leaf_lane_phases;
+    /* PRT_TRACE_EXACT | PRT_TRACE_COUNT: triangle tests whose FP32 decision was inside its error
+     * bound and were decided in place with the FP64 formula (flagged_rays counts the rays that
+     * still needed the FP64 replay afterwards) */
+    uint64_t f64_decisions;
 } prt_counters;
 
 /* trace flags */
-#define PRT_TRACE_EXACT 1u /* FP32 pass flags low-margin decisions, FP64 replay of the
-                              reference's Moller-Trumbore resolves them (bit-exact ids) */
+#define PRT_TRACE_EXACT 1u /* bit-exact ids: the FP32 traversal carries forward error bounds; a triangle
+                              whose decision is inside its bound is decided with the reference's FP64
+                              Moller-Trumbore in place, rays that still cannot be ordered are replayed
+                              in FP64; (t,u,v) of every hit = the reference's FP64 values rounded to
+                              f32.  Same persistent kernel as the plain mode (about 0.88x its rate). */
 #define PRT_TRACE_COUNT 2u /* counter-instrumented twin kernel (roofline N_node / N_tri) */
 #define PRT_TRACE_BRUTE 4u /* ignore the BVH: test every triangle (Aggregator semantics,
                               accelerators/aggregator.py:74-85) */
@@ -140,7 +149,7 @@ typedef struct {
     float cost_node;        /* SAH traversal cost, default 1.0 */
     float cost_tri;         /* SAH intersection cost, default 2.0 */
     uint32_t rotations;     /* number of bottom-up SAH rotation passes during refit (0 = none, default 1) */
-    uint32_t treelets;      /* 1 (default): every maximal subtree of <= 64 triangles of the Morton
+    uint32_t treelets;      /* 1 (default): every maximal subtree of <= 128 triangles of the Morton
                                hierarchy is rebuilt with binned SAH before refit; 0 = plain LBVH */
 } prt_bvh_options;
 

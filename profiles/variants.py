@@ -9,15 +9,21 @@ VDIR = os.path.join(ROOT, "pyrenderer_b200", "variants")
 # -6 %, PRMT+FADD byte->float instead of I2F.U8 -8 %, L1 prefetch of the far child 0 %, smem stack
 # depth 8/12/16 no effect -- none of them is in the tree any more; add -D switches here to try new ones.
 VARIANTS = {
-    "t64": ("-DPRT_TREELET=64",),
-    "t128": ("-DPRT_TREELET=128",),
-    "t192": ("-DPRT_TREELET=192",),
+    "n8": ("-DPRT_MIN_BLOCKS_EXACT=8",),
+    "n7": ("-DPRT_MIN_BLOCKS_EXACT=7",),
+    "n6": ("-DPRT_MIN_BLOCKS_EXACT=6",),
+    "i6": ("-DPRT_MIN_BLOCKS_EXACT=6", "-DPRT_EXACT_INLINE=1"),
 }
 if sys.argv[1] == "build":
     from pyrenderer_b200 import build
     os.makedirs(VDIR, exist_ok=True)
     for name, defs in VARIANTS.items():
         print(name, build.build(force=True, defines=defs, out=os.path.join(VDIR, name + ".so")))
+elif sys.argv[1] == "exact":
+    for name in VARIANTS:
+        env = dict(os.environ, PRT_LIB=os.path.join(VDIR, name + ".so"))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "prof_exact.py")] + sys.argv[2:], env=env, capture_output=True, text=True)
+        print(f"[{name}] " + " | ".join(l for l in r.stdout.splitlines() if l.startswith("{")) + ("" if r.returncode == 0 else " ERR " + r.stderr[-300:]), flush=True)
 else:
     for name in VARIANTS:
         env = dict(os.environ, PRT_LIB=os.path.join(VDIR, name + ".so"))

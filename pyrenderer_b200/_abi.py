@@ -55,7 +55,7 @@ class PrtCounters(C.Structure):
                 ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("flagged_rays", C.c_uint64), ("paths", C.c_uint64), ("warp_iters", C.c_uint64),
                 ("node_lane_iters", C.c_uint64), ("leaf_phases", C.c_uint64),
-                ("leaf_lane_phases", C.c_uint64)]
+                ("leaf_lane_phases", C.c_uint64), ("f64_decisions", C.c_uint64)]
 
 
 EXPORTS = [
@@ -109,7 +109,7 @@ def load():
     for name in EXPORTS:
         if name not in ("prt_destroy", "prt_last_error"):
             getattr(lib, name).restype = C.c_int
-    if lib.prt_abi_version() != 2:
+    if lib.prt_abi_version() != 3:
         raise PrtError("libprt.so ABI version mismatch")
     _LIB = lib
     return lib
@@ -130,10 +130,12 @@ def _dev_ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def _stream_ptr(stream):
+def _stream_ptr(stream, device=None):
+    """cudaStream_t of ``stream`` (torch stream or raw handle); None = torch's current stream ON THE
+    CONTEXT'S DEVICE (a stream of another device would be an invalid handle there)."""
     if stream is None:
         import torch
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream(device)
     return C.c_void_p(getattr(stream, "cuda_stream", stream))
 
 
@@ -178,7 +180,7 @@ class Context:
 
     def set_triangles_dev(self, verts_dev, nt, stream=None):
         self._check(self.lib.prt_scene_set_triangles_dev(self.h, _dev_ptr(verts_dev), int(nt),
-                                                         _stream_ptr(stream)))
+                                                         _stream_ptr(stream, self.device)))
 
     def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=2.0, rotations=1, treelets=1):
         opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations), int(treelets))
@@ -202,19 +204,19 @@ class Context:
                       stream=None):
         self._check(self.lib.prt_generate_rays(self.h, int(seed), int(s0), int(s1), 1 if jitter else 0,
                                                float(tmin), float(tmax), _dev_ptr(rays_dev),
-                                               _stream_ptr(stream)))
+                                               _stream_ptr(stream, self.device)))
 
     def trace_closest(self, rays_dev, n, hits_dev, flags=0, stream=None):
         self._check(self.lib.prt_trace_closest(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(hits_dev),
-                                               int(flags), _stream_ptr(stream)))
+                                               int(flags), _stream_ptr(stream, self.device)))
 
     def trace_any(self, rays_dev, n, occluded_dev, flags=0, stream=None):
         self._check(self.lib.prt_trace_any(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(occluded_dev),
-                                           int(flags), _stream_ptr(stream)))
+                                           int(flags), _stream_ptr(stream, self.device)))
 
     def trace_all(self, rays_dev, n, counts_dev, sums_dev, flags=0, stream=None):
         self._check(self.lib.prt_trace_all(self.h, _dev_ptr(rays_dev), int(n), _dev_ptr(counts_dev),
-                                           _dev_ptr(sums_dev), int(flags), _stream_ptr(stream)))
+                                           _dev_ptr(sums_dev), int(flags), _stream_ptr(stream, self.device)))
 
     def trace_closest_host(self, rays, flags=0, out=None):
         """``out``: optional HIT_DTYPE array to receive the hits (page-locked for speed)."""
@@ -246,11 +248,11 @@ class Context:
 
     def render(self, params, accum_dev, prim_ids_dev=None, stream=None):
         self._check(self.lib.prt_render(self.h, C.byref(params), _dev_ptr(accum_dev),
-                                        _dev_ptr(prim_ids_dev), _stream_ptr(stream)))
+                                        _dev_ptr(prim_ids_dev), _stream_ptr(stream, self.device)))
 
     def trace_paths(self, rays_dev, n, params, radiance_dev, prim_ids_dev=None, stream=None):
         self._check(self.lib.prt_trace_paths(self.h, _dev_ptr(rays_dev), int(n), C.byref(params),
-                                             _dev_ptr(radiance_dev), _dev_ptr(prim_ids_dev), _stream_ptr(stream)))
+                                             _dev_ptr(radiance_dev), _dev_ptr(prim_ids_dev), _stream_ptr(stream, self.device)))
 
     def set_path_log(self, segments_dev=None, count_dev=None):
         """segments_dev: torch f32 [capacity, 8] (prt_segment records), count_dev: torch i32/u32 [1];

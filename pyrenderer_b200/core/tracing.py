@@ -28,8 +28,12 @@ def new_accum(camera, device=0):
 
 def render(scene, camera, spp=8, max_depth=5, seed=1, spp_begin=0, rr_start=RR_OFF, device=0,
            accum=None, want_prim_ids=False, light_color=LIGHT_COLOR, stream=None,
-           exact_primary=False, physical=False):
+           exact_primary=True, physical=False):
     """Add samples [spp_begin, spp_begin+spp) to ``accum`` (created if None).
+
+    ``exact_primary`` (default): bounce 0 runs in PRT_TRACE_EXACT mode, so primary-hit triangle
+    ids are bit-exact against the reference's intersection code (mathematics/intersection.py:42-65,
+    106-116); it costs ~2 % of a depth-8 Cornell render (bench.py ``render.exact_primary_cost``).
 
     ``physical`` selects the physically-based estimator (PRT_RENDER_PHYSICAL: scene emission,
     MIS of light and BSDF sampling -- comparable with Tungsten's render of the same scene)
@@ -99,21 +103,41 @@ def shard_samples(spp, rank, world):
     return (spp * rank) // world, (spp * (rank + 1)) // world
 
 
-def render_distributed(scene, camera, spp, max_depth=5, seed=1, rr_start=RR_OFF, device=0,
-                       accum=None, group=None, render_fn=None):
-    """Every rank renders its sample shard; one all-reduce sums the buffers.
+def default_device():
+    """Device of this rank: LOCAL_RANK under torchrun, else torch's current CUDA device."""
+    import os
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    torch = _torch()
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
 
-    ``render_fn`` (default :func:`render`) exists so the sharding + reduction logic can be
-    exercised without a GPU (tests/test_distributed_cpu.py plugs the CPU oracle in over gloo).
+
+def render_distributed(scene, camera, spp, max_depth=5, seed=1, rr_start=RR_OFF, device=None,
+                       accum=None, group=None, render_fn=None, spp_begin=0, **render_kw):
+    """Samples [spp_begin, spp_begin+spp) of every pixel, sharded over the ranks of ``group``
+    (SURVEY 8e): every rank renders its contiguous sample range into a FRESH buffer, ONE all-reduce
+    sums the shards, and the sum is added to ``accum`` (created if None) -- so a progressive or
+    resumed call with a non-empty ``accum`` adds exactly ``spp`` samples on every rank.
+
+    ``device`` defaults to this rank's device (LOCAL_RANK).  ``render_fn`` (default
+    :func:`render`) exists so the sharding + reduction logic can be exercised without a GPU
+    (tests/test_distributed_cpu.py plugs the CPU oracle in over gloo).
     """
     import torch.distributed as dist
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    if device is None:
+        device = default_device()
     s0, s1 = shard_samples(spp, rank, world)
-    accum = (render_fn or render)(scene, camera, spp=s1 - s0, max_depth=max_depth, seed=seed,
-                                  spp_begin=s0, rr_start=rr_start, device=device, accum=accum)
+    shard = (render_fn or render)(scene, camera, spp=s1 - s0, max_depth=max_depth, seed=seed,
+                                  spp_begin=spp_begin + s0, rr_start=rr_start, device=device, accum=None,
+                                  **render_kw)
     if world > 1:
-        dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(shard, op=dist.ReduceOp.SUM, group=group)
+    if accum is None:
+        return shard
+    accum += shard
     return accum
 
 

@@ -135,29 +135,45 @@ struct PlaneEval {
         const float a0 = scale * idir, b0 = (origin - ro) * idir;
         if (FOLD) { a = a0 * 32768.0f; b = b0 - a; } else { a = a0; b = b0; }
     }
+    // EXACT: bound of |computed - exact| for any plane of this axis, in units of u = 2^-24.
+    // Unfolded (t = q*a + b, a = s*idir exact up to idir's error e_i <= 2u, b two roundings + e_i):
+    //   <= 3u*255|a| + 5u|b|  ->  8u (|b| + 255|a|).
+    // Folded (a' = 2^15 a exact, b' = fl(b - a'), t = fl(f*a' + b')): the extra rounding of b' adds
+    //   u (|b| + |a'|), in the stored constants <= 8u (|b'| + |a'|)  ->  11u (|b'| + |a'|),
+    //   i.e. 2 % of one quantisation step: boxes grow by nothing that shows in the visit count.
+    __device__ __forceinline__ float err_bound() const {
+        return FOLD ? 11.0f * kUnit * (fabsf(b) + fabsf(a)) : 8.0f * kUnit * (fabsf(b) + 255.0f * fabsf(a));
+    }
     __device__ __forceinline__ float q(uint32_t w, int c) const {  // byte c -> the float the FMA consumes
         if (FOLD) return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t)(c << 4)));
         return qf(w, c);
     }
-    __device__ __forceinline__ void eval4(uint32_t w, float t[4]) const {  // the four children's planes of one word
+    // the four children's planes of one word; `shift` (EXACT) moves them by the error bound
+    template <bool SHIFT>
+    __device__ __forceinline__ void eval4(uint32_t w, float t[4], float shift) const {
+        const float bb = SHIFT ? b + shift : b;
 #if PRT_FMA2
-        fma2_bcast(q(w, 0), q(w, 1), a, b, t[0], t[1]);
-        fma2_bcast(q(w, 2), q(w, 3), a, b, t[2], t[3]);
+        fma2_bcast(q(w, 0), q(w, 1), a, bb, t[0], t[1]);
+        fma2_bcast(q(w, 2), q(w, 3), a, bb, t[2], t[3]);
 #else
 #pragma unroll
-        for (int c = 0; c < 4; ++c) t[c] = fmaf(q(w, c), a, b);
+        for (int c = 0; c < 4; ++c) t[c] = fmaf(q(w, c), a, bb);
 #endif
     }
 };
 
-// Slab test of the four children: h.t[c] = entry distance, +inf for a miss.  EXACT widens every
-// interval by the forward error bound of t = q*a + b so that no box the exact ray touches is missed.
+// Slab test of the four children: h.t[c] = entry distance, +inf for a miss.  EXACT moves every
+// plane distance outwards by the forward error bound of t = q*a + b OF ITS OWN AXIS, so that no
+// box the exact ray touches is missed.  (Per axis, not one bound for the whole test: for a ray
+// nearly parallel to an axis that axis has |idir| ~ 1e5 and an error bound larger than the other
+// two slabs; applied to all three it made 3 % of the rays visit far too much and a handful
+// traverse the whole tree -- a 9 ms tail on a 10 ms launch.)
 template <bool EXACT>
 __device__ __forceinline__ void node_test4(const Node64* __restrict__ node, const RayBox& r,
                                            float tmin, float tmax, NodeHits& h) {
     uint4 w0, w1, w2, w3;
     ldg_node(node, w0, w1, w2, w3);
-    constexpr int kFold = EXACT ? 0 : PRT_QCONV_AXES;
+    constexpr int kFold = PRT_QCONV_AXES;
     const PlaneEval<(kFold > 2)> px(__uint_as_float(w0.w), __uint_as_float(w0.x), r.o.x, r.idir.x);
     const PlaneEval<(kFold > 1)> py(__uint_as_float(w1.x), __uint_as_float(w0.y), r.o.y, r.idir.y);
     const PlaneEval<(kFold > 0)> pz(__uint_as_float(w1.y), __uint_as_float(w0.z), r.o.z, r.idir.z);
@@ -165,22 +181,19 @@ __device__ __forceinline__ void node_test4(const Node64* __restrict__ node, cons
     const uint32_t ny = r.negy ? w2.y : w2.x, fy = r.negy ? w2.x : w2.y;
     const uint32_t nz = r.negz ? w2.w : w2.z, fz = r.negz ? w2.z : w2.w;
     h.ref[0] = w3.x; h.ref[1] = w3.y; h.ref[2] = w3.z; h.ref[3] = w3.w;
-    float m = 0.0f;
-    if (EXACT)
-        m = 8.0f * kUnit * (fmaxf(fmaxf(fabsf(px.b) + 255.0f * fabsf(px.a), fabsf(py.b) + 255.0f * fabsf(py.a)),
-                                  fabsf(pz.b) + 255.0f * fabsf(pz.a)));
+    const float mx = EXACT ? px.err_bound() : 0.0f, my = EXACT ? py.err_bound() : 0.0f, mz = EXACT ? pz.err_bound() : 0.0f;
     const float inf = __int_as_float(0x7f800000);
     float xn[4], xf[4], yn[4], yf[4], zn[4], zf[4];
-    px.eval4(nx, xn); px.eval4(fx, xf);
-    py.eval4(ny, yn); py.eval4(fy, yf);
-    pz.eval4(nz, zn); pz.eval4(fz, zf);
+    px.template eval4<EXACT>(nx, xn, -mx); px.template eval4<EXACT>(fx, xf, mx);
+    py.template eval4<EXACT>(ny, yn, -my); py.template eval4<EXACT>(fy, yf, my);
+    pz.template eval4<EXACT>(nz, zn, -mz); pz.template eval4<EXACT>(fz, zf, mz);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float tn = fmaxf(fmaxf(xn[c], yn[c]), fmaxf(zn[c], tmin));
         float tf = fminf(fminf(xf[c], yf[c]), fminf(zf[c], tmax));
-        if (EXACT) { tn -= m; tf += m; }
         // absent children carry inverted planes AND kNoChild: the planes alone are not proof
         // (255*a + b can round to b for a tiny record far away)
+        // (children 0 and 1 always exist: the one-triangle scene pads slot 1 with an empty leaf)
         h.t[c] = (tn <= tf && (c < 2 || h.ref[c] != kNoChild)) ? tn : inf;
     }
 }

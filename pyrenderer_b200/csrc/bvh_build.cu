@@ -45,7 +45,9 @@ struct BuildBuffers {
     int2* range = nullptr;          // [N-1] sorted positions covered by each internal node (treelets)
     int* roots = nullptr;           // [N-1] treelet roots
     unsigned int* n_roots = nullptr;
+    cudaEvent_t ev[7] = {};         // phase timing; destroyed with the buffers (also on the error paths)
     void free_all() {
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
         cudaFree(sort_tmp); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(bmin);
         cudaFree(bmax); cudaFree(tcount); cudaFree(icount); cudaFree(collapsed); cudaFree(flags);
@@ -687,10 +689,14 @@ __global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nod
     const float o[3] = {lo.x, lo.y, lo.z};
     const float ext[3] = {hi.x - lo.x, hi.y - lo.y, hi.z - lo.z};
     float clo[4][3], chi[4][3];
-    clo[0][0] = lo.x; clo[0][1] = lo.y; clo[0][2] = lo.z;
-    chi[0][0] = hi.x; chi[0][1] = hi.y; chi[0][2] = hi.z;
-    const uint32_t ref[4] = {kLeafFlag | 1u, kNoChild, kNoChild, kNoChild};
-    write_record(nodes, o, ext, clo, chi, ref, 1);
+    // node_test4 does not test slots 0 and 1 for kNoChild: slot 1 is an EMPTY leaf (count 0) with the
+    // same box, so a ray that "hits" it visits nothing
+    for (int c = 0; c < 2; ++c) {
+        clo[c][0] = lo.x; clo[c][1] = lo.y; clo[c][2] = lo.z;
+        chi[c][0] = hi.x; chi[c][1] = hi.y; chi[c][2] = hi.z;
+    }
+    const uint32_t ref[4] = {kLeafFlag | 1u, kLeafFlag, kNoChild, kNoChild};
+    write_record(nodes, o, ext, clo, chi, ref, 2);
     write_tri(verts, 0, 0, tri_a, tri_b);
 }
 
@@ -725,8 +731,8 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         if (stats) *stats = st;
         return PRT_OK;
     }
-    cudaEvent_t ev[7];
-    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEvent_t* ev = B.ev;
+    for (auto& e : B.ev) BUILD_TRY(cudaEventCreate(&e));
     const size_t nn = 2 * (size_t)nt - 1;
     BUILD_TRY(cudaMalloc(&ctx->tri_a, sizeof(uint4) * 2 * (size_t)nt));
     BUILD_TRY(cudaMalloc(&ctx->tri_b, sizeof(float2) * (size_t)nt));
@@ -837,7 +843,6 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     n_rec = n_wide;
     float ms[6];
     for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
-    for (auto& e : ev) cudaEventDestroy(e);
     st.n_nodes = n_rec;
     st.sah_cost = (n > 1 && root_hi.w > 0.f) ? root_lo.w / root_hi.w : 0.f;
     st.ms_morton = ms[0]; st.ms_sort = ms[1]; st.ms_hierarchy = ms[2]; st.ms_refit = ms[3];

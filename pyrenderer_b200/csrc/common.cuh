@@ -46,6 +46,7 @@ struct SceneDev {
 struct Counters {
     unsigned long long rays_closest, rays_shadow, node_visits, tri_tests, flagged_rays, paths;
     unsigned long long warp_iters, node_lane_iters, leaf_phases, leaf_lane_phases;  // persist.cuh utilisation (COUNT)
+    unsigned long long f64_decisions;  // EXACT + COUNT: triangle tests decided in place in FP64
 };
 
 // ---- small vector helpers ---------------------------------------------------

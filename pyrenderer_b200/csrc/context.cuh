@@ -39,7 +39,7 @@ struct prt_ctx {
     static constexpr unsigned kFetchRing = 32;
     unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
     unsigned fetch_next = 0;
-    int grid_persist = 0;
+    int grid_persist = 0, grid_persist_exact = 0;  // resident CTAs of the plain / EXACT persistent kernels
     int refill_idle = 0, leaf_batch = 8;  // refill_idle 0 = by scene size (profiles/r1_sweeps.txt)
     int fetch_chunk = 0;                  // ray indices reserved per atomic; 0 = default (32)
 

@@ -183,6 +183,64 @@ __device__ __forceinline__ int tri_watertight_fast(const RayWF& r, float3 p0, fl
     return 1;
 }
 
+// ---- exact-mode variant of the throughput test ----------------------------------------------
+// tri_watertight_fast with forward error bounds (u = 2^-24), used by the persistent EXACT
+// traversal.  It reports `uncertain` whenever the decision -- inside / outside, t in range, t
+// against the current best -- could differ from the exact-arithmetic one; the caller then decides
+// that triangle with mt_f64.  The bounds are built so that they scale with the triangle's
+// footprint AROUND THE RAY, not with its distance from the ray origin:
+//   * sheared coordinate of vertex P: |dPx|, |dPy| <= 5u nP, nP = |P.x|+|P.y|+|P.z| (P = p - o; the
+//     shear coefficients are <= 1 in magnitude, Sz <= 1 ulp, Sx, Sy <= 1.5 ulp from rcp_fast);
+//     e_P = 12u nP also absorbs the roundings of the two products of an edge function;
+//   * U = Cx By - Cy Bx:  |dU| <= rC e_B + e_C (rB + 2 e_B), rP = |Px| + |Py|  -- ~ distance x
+//     footprint, where the round-1 bound (M M) was ~ distance^2 (60x larger on the 1M soup: it
+//     flagged 1 % of the rays and left 2.7 % of slack on the culling distance);
+//   * t = Az + (V (Bz-Az) + W (Cz-Az)) / det: the ray origin cancels in Bz - Az, so the error of
+//     the quotient scales with the triangle's depth extent; dt ~ 25u |t| for an ordinary hit.
+// A result with dt > 2^-10 |t| (grazing) is reported uncertain, so the culling slack stays small.
+__device__ __forceinline__ int tri_watertight_fast_exact(const RayWF& r, float3 p0, float3 p1, float3 p2,
+                                                         float t_lo, float bound, float bound_err,
+                                                         TriHit& h, bool& uncertain) {
+    const float3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
+    const float Ax = dot3f(A, r.cx), Ay = dot3f(A, r.cy);
+    const float Bx = dot3f(B, r.cx), By = dot3f(B, r.cy);
+    const float Cx = dot3f(C, r.cx), Cy = dot3f(C, r.cy);
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    constexpr float kE = 12.0f * kUnit;
+    const float eA = kE * (fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
+    const float eB = kE * (fabsf(B.x) + fabsf(B.y) + fabsf(B.z));
+    const float eC = kE * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z));
+    const float rA = fabsf(Ax) + fabsf(Ay), rB = fabsf(Bx) + fabsf(By), rC = fabsf(Cx) + fabsf(Cy);
+    const float eU = fmaf(rC, eB, eC * fmaf(2.0f, eB, rB));
+    const float eV = fmaf(rA, eC, eA * fmaf(2.0f, eC, rC));
+    const float eW = fmaf(rB, eA, eB * fmaf(2.0f, eA, rA));
+    const bool neg = (U < -eU) || (V < -eV) || (W < -eW);
+    const bool pos = (U > eU) || (V > eV) || (W > eW);
+    if (neg && pos) return 0;  // certainly outside
+    const float det = U + V + W;
+    const float eDet = eU + eV + eW + 4.0f * kUnit * (fabsf(U) + fabsf(V) + fabsf(W));
+    if (!(fabsf(det) > eDet)) { uncertain = true; return 0; }
+    const float Az = dot3f(A, r.cz), Bz = dot3f(B, r.cz), Cz = dot3f(C, r.cz);
+    const float dB = Bz - Az, dC = Cz - Az;
+    const float Tp = fmaf(V, dB, W * dC);
+    const float inv = rcp_fast(det);
+    const float tp = Tp * inv;
+    const float t = Az + tp;
+    const float e_dz = 6.0f * kUnit * (fabsf(Az) + fabsf(Bz) + fabsf(Cz));
+    const float eTp = (fabsf(V) + fabsf(W)) * e_dz + eV * fabsf(dB) + eW * fabsf(dC) +
+                      2.0f * kUnit * (fabsf(V * dB) + fabsf(W * dC));
+    const float dt = 1.001f * (eTp + fabsf(tp) * eDet) * fabsf(inv) + 6.0f * kUnit * (fabsf(Az) + fabsf(tp));
+    if (t < t_lo - dt || t > bound + dt + bound_err) return 0;  // certainly out of range
+    const bool edge_sure = (fabsf(U) > eU) && (fabsf(V) > eV) && (fabsf(W) > eW);
+    const bool range_sure = (t >= t_lo + dt) && (t <= bound - dt - bound_err);
+    const bool tight = dt <= 0.0009765625f * fabsf(t);
+    if (!edge_sure || !range_sure || !tight) { uncertain = true; return 0; }
+    h.t = t; h.u = V * inv; h.v = W * inv; h.dt = dt;
+    return 1;  // (edge_sure and not certainly outside => all three edge functions share a sign)
+}
+
 // ---- FP64 replay of the reference kernel -------------------------------------
 __device__ __forceinline__ double ddot3(const double* x, const double* y) {
     return __dadd_rn(__dadd_rn(__dmul_rn(x[0], y[0]), __dmul_rn(x[1], y[1])), __dmul_rn(x[2], y[2]));

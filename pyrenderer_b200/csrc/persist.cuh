@@ -16,8 +16,15 @@
 //     their leaves together.  Record visits are 60 % of the issued instructions and
 //     run at 19..26 of 32 lanes; they are what is kept convergent.
 //
-// IO is a functor: load(k, ro, rd, tag) / store(tag, t, u, v, gid); it binds this
+// IO is a functor: load(k, ro, rd, tag) / store(tag, t, u, v, gid) / flag(tag); it binds this
 // loop to the API ray arrays or to the wavefront queues.
+//
+// EXACT (PRT_TRACE_EXACT on this same loop): the triangle test carries forward error bounds
+// (tri_watertight_fast_exact), the box test is widened by its own bound (node_test4<true>),
+// culling keeps every candidate closer than best t + its error bound, and a ray whose answer
+// could depend on an FP32 rounding is handed to io.flag() instead of io.store(); the caller
+// re-traces flagged rays in FP64 (resolve_kernel).  Unflagged results are the exact-arithmetic
+// winners, i.e. the reference's (mathematics/intersection.py:42-65,106-116).
 #pragma once
 #include "bvh.cuh"
 #include "traverse.cuh"
@@ -36,7 +43,47 @@ namespace prt {
 // leaf_batch: intersect leaves when at least this many lanes are parked); defaults in context.cuh,
 // overridable with PRT_REFILL_IDLE / PRT_LEAF_BATCH for tuning sweeps.
 
-template <int MODE, bool COUNT, class IO>
+// EXACT slow path: one triangle whose FP32 test was inside its error bound, decided with the
+// reference's FP64 formula (mt_f64) and ordered against the current best by the reference's
+// (t, id) rule.  Returns 0 = not a hit / not better, 1 = `best` updated, 2 = cannot decide here
+// (the current best is not reproduced in FP64): flag the ray.  Kept out of line so that its FP64
+// temporaries do not count against the registers of the traversal loop.
+struct ExactBest { float t, u, v, dt; int gid; };
+#ifndef PRT_EXACT_INLINE
+#define PRT_EXACT_INLINE 0
+#endif
+template <int MODE>
+#if PRT_EXACT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+int exact_decide_tri(const SceneDev& sc, float3 p0, float3 p1, float3 p2, int gid, float4 ro, float4 rd, ExactBest& best) {
+    const double o64[3] = {(double)ro.x, (double)ro.y, (double)ro.z};
+    const double d64[3] = {(double)rd.x, (double)rd.y, (double)rd.z};
+    double t64, u64, v64;
+    if (!mt_f64(p0, p1, p2, o64, d64, (double)ro.w, (double)rd.w, t64, u64, v64)) return 0;
+    if (MODE == MODE_ANY) { best.t = (float)t64; best.gid = gid; return 1; }
+    bool take = best.gid < 0 || t64 < (double)best.t - (double)best.dt;
+    int rc = 0;
+    if (!take && !(t64 > (double)best.t + (double)best.dt)) {
+        // near tie with the current best: order the two by the reference's (t, id)
+        const float4* tp = sc.verts_gid + 3ull * (uint32_t)best.gid;
+        double tb, ub, vb;
+        if (!mt_f64(xyz(__ldg(tp)), xyz(__ldg(tp + 1)), xyz(__ldg(tp + 2)), o64, d64, (double)ro.w, (double)rd.w, tb, ub, vb))
+            return 2;
+        take = t64 < tb || (t64 == tb && gid < best.gid);
+        if (!take) { best.t = (float)tb; best.u = (float)ub; best.v = (float)vb; best.dt = 2.0f * kUnit * fabsf(best.t); rc = 1; }
+    }
+    if (take) {
+        best.t = (float)t64; best.u = (float)u64; best.v = (float)v64; best.gid = gid;
+        best.dt = 2.0f * kUnit * fabsf(best.t);
+        rc = 1;
+    }
+    return rc;
+}
+
+template <int MODE, bool COUNT, bool EXACT, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsigned int* fetch,
                                                  unsigned int n, uint2* stack_col, Counters* ctr) {
     const unsigned FULL = 0xffffffffu;
@@ -49,9 +96,11 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
     RayWF rw;
     RayBox rb;
     float tmin = 0.f, tmax = 0.f, bt = 0.f, bu = 0.f, bv = 0.f;
+    float bdt = 0.f;       // EXACT: error bound of bt
+    bool flagged = false;  // EXACT: this ray needs the FP64 replay
     int bgid = -1, sp = 0;
     uint32_t cur = kDone, tag = 0;
-    unsigned long long c_nodes = 0, c_tris = 0, c_rays = 0;
+    unsigned long long c_nodes = 0, c_tris = 0, c_rays = 0, c_f64 = 0;
     unsigned long long c_iters = 0, c_nlanes = 0, c_lphases = 0, c_llanes = 0;  // lane 0 only
 
     if (sc.n_nodes == 0) {  // empty scene: everything misses
@@ -100,6 +149,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     rb = make_raybox_fast(o, d);
                     tmin = ro.w; tmax = rd.w;
                     bt = tmax; bu = 0.f; bv = 0.f; bgid = -1;
+                    bdt = 0.f; flagged = false;
                     cur = 0;
                     sstack_reset(ovf, sp);
                     has_ray = true;
@@ -117,11 +167,12 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
         // ---- one record visit for every lane that is at an internal record
 #pragma unroll
         for (int rep = 0; rep < PRT_VISITS_PER_ITER; ++rep) {
-            const float bound = MODE == MODE_CLOSEST ? bt : tmax;
+            // EXACT: a candidate closer than best t + its error bound must still be visited
+            const float bound = MODE == MODE_CLOSEST ? (EXACT ? bt + bdt : bt) : tmax;
             if (has_ray && !(cur & kLeafFlag)) {
                 if (COUNT) ++c_nodes;
                 NodeHits h;
-                node_test4<false>(sc.nodes + cur, rb, tmin, bound, h);
+                node_test4<EXACT>(sc.nodes + cur, rb, tmin, bound, h);
                 cur = MODE == MODE_ANY ? descend_any(h, saddr, ovf, sp) : descend(h, saddr, ovf, sp, bound);
             }
         }
@@ -142,20 +193,43 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     load_tri<false>(sc, start + k, p0, p1, p2, gid);
                     if (COUNT) ++c_tris;
                     TriHit h;
-                    if (tri_watertight_fast(rw, p0, p1, p2, tmin, MODE == MODE_CLOSEST ? bt : tmax, h)) {
+                    int hit;
+                    if constexpr (EXACT) {
+                        bool unc = false;
+                        hit = tri_watertight_fast_exact(rw, p0, p1, p2, tmin, MODE == MODE_CLOSEST ? bt : tmax,
+                                                        MODE == MODE_CLOSEST ? bdt : 0.0f, h, unc);
+                        if (unc) {
+                            // The FP32 decision is inside its error bound: decide THIS triangle with the
+                            // reference's own FP64 formula, in place (rare).  Only what still cannot be
+                            // ordered goes to the FP64 replay.
+                            float4 ro4, rd4;
+                            io.reload(tag, ro4, rd4);
+                            if (COUNT) ++c_f64;
+                            ExactBest eb{bt, bu, bv, bdt, bgid};
+                            const int rc = exact_decide_tri<MODE>(sc, p0, p1, p2, gid, ro4, rd4, eb);
+                            bt = eb.t; bu = eb.u; bv = eb.v; bdt = eb.dt; bgid = eb.gid;
+                            if (rc == 2) { flagged = true; stop = true; break; }
+                            if (rc == 1 && MODE == MODE_ANY) { stop = true; break; }
+                            continue;
+                        }
+                    } else {
+                        hit = tri_watertight_fast(rw, p0, p1, p2, tmin, MODE == MODE_CLOSEST ? bt : tmax, h);
+                    }
+                    if (hit) {
                         if (MODE == MODE_CLOSEST) {
-                            if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; }
+                            if (h.t < bt || bgid < 0 || gid < bgid) { bt = h.t; bu = h.u; bv = h.v; bgid = gid; bdt = h.dt; }
                         } else {
                             bt = h.t; bgid = gid; stop = true;
                             break;
                         }
                     }
                 }
-                cur = stop ? kDone : sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? bt : tmax);
+                cur = stop ? kDone : sstack_pop_live(saddr, ovf, sp, MODE == MODE_CLOSEST ? (EXACT ? bt + bdt : bt) : tmax);
             }
         }
         if (has_ray && cur == kDone) {
-            io.store(tag, bt, bu, bv, bgid);
+            if (EXACT && flagged) io.flag(tag);
+            else io.store(tag, bt, bu, bv, bgid);
             has_ray = false;
         }
     }
@@ -164,6 +238,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
             c_nodes += __shfl_down_sync(FULL, c_nodes, o);
             c_tris += __shfl_down_sync(FULL, c_tris, o);
             c_rays += __shfl_down_sync(FULL, c_rays, o);
+            c_f64 += __shfl_down_sync(FULL, c_f64, o);
         }
         if (lane == 0) {
             atomicAdd(&ctr->node_visits, c_nodes);
@@ -173,6 +248,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
             atomicAdd(&ctr->node_lane_iters, c_nlanes);
             atomicAdd(&ctr->leaf_phases, c_lphases);
             atomicAdd(&ctr->leaf_lane_phases, c_llanes);
+            if (EXACT) atomicAdd(&ctr->f64_decisions, c_f64);
         }
     }
 }

@@ -7,7 +7,24 @@
 
 #include "context.cuh"
 
-static char g_create_error[512] = "";
+// text of the last prt_create failure, per calling thread (prt_last_error(NULL))
+static thread_local char g_create_error[512] = "";
+
+// Every entry point runs on the context's device and puts the caller's current device back on
+// return (the caller may be torch, with another device current).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev == dev) return cudaSuccess;
+        e = cudaSetDevice(dev);
+        switched = e == cudaSuccess;
+        return e;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 namespace prt {
 
@@ -83,7 +100,9 @@ using namespace prt;
 
 #define CHECK_CTX(ctx) \
     do { if (!(ctx)) return PRT_ERR_INVALID; } while (0)
-#define USE_DEVICE(ctx) PRT_CUDA_TRY(ctx, cudaSetDevice((ctx)->device))
+#define USE_DEVICE(ctx)  \
+    DeviceGuard _guard; \
+    PRT_CUDA_TRY(ctx, _guard.enter((ctx)->device))
 
 extern "C" {
 
@@ -108,10 +127,20 @@ int prt_create(int device, prt_ctx** out) {
     prt_ctx* c = new (std::nothrow) prt_ctx();
     if (!c) return PRT_ERR_NOMEM;
     c->device = device;
-    if (const char* v = getenv("PRT_REFILL_IDLE")) c->refill_idle = atoi(v) > 0 ? atoi(v) : c->refill_idle;
-    if (const char* v = getenv("PRT_LEAF_BATCH")) c->leaf_batch = atoi(v) > 0 ? atoi(v) : c->leaf_batch;
-    if (const char* v = getenv("PRT_FETCH_CHUNK")) c->fetch_chunk = atoi(v) > 0 ? atoi(v) : c->fetch_chunk;
-    e = cudaSetDevice(device);
+    // tuning knobs (profiles/sweep.py), clamped to what the persistent loop can make progress with:
+    // refill_idle > 32 would never refill (the kernel would spin), leaf_batch > 32 only ever fires
+    // through the "nobody walks records" rule, a fetch chunk of 0 reserves nothing
+    auto knob = [](const char* name, int lo, int hi, int dflt) {
+        const char* v = getenv(name);
+        if (!v) return dflt;
+        const int x = atoi(v);
+        return x < lo ? dflt : (x > hi ? hi : x);
+    };
+    c->refill_idle = knob("PRT_REFILL_IDLE", 1, 32, c->refill_idle);
+    c->leaf_batch = knob("PRT_LEAF_BATCH", 1, 32, c->leaf_batch);
+    c->fetch_chunk = knob("PRT_FETCH_CHUNK", 1, 4096, c->fetch_chunk);
+    DeviceGuard guard;
+    e = guard.enter(device);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) {
@@ -138,7 +167,8 @@ int prt_create(int device, prt_ctx** out) {
 
 void prt_destroy(prt_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard;
+    guard.enter(ctx->device);
     wavefront_free(ctx);
     free_scene(ctx);
     cudaFree(ctx->counters); cudaFree(ctx->flag_list); cudaFree(ctx->flag_count);
@@ -161,9 +191,15 @@ int prt_scene_set_triangles(prt_ctx* ctx, const float* verts_host, const float* 
     if (nl && !light_tris_host) { ctx->set_error("scene: light_tris == NULL"); return PRT_ERR_INVALID; }
     for (uint32_t i = 0; i < nl; ++i)
         if (light_tris_host[i] >= nt) { ctx->set_error("scene: light triangle %u out of range", light_tris_host[i]); return PRT_ERR_INVALID; }
-    if (tri_material_host && mats_host)
+    if (tri_material_host) {
+        // without a material table the scene gets ONE default material: only index 0 exists then
+        const uint32_t nm_eff = (mats_host && nm) ? nm : 1u;
         for (uint32_t i = 0; i < nt; ++i)
-            if (tri_material_host[i] >= nm) { ctx->set_error("scene: material index %u out of range", tri_material_host[i]); return PRT_ERR_INVALID; }
+            if (tri_material_host[i] >= nm_eff) {
+                ctx->set_error("scene: material index %u of triangle %u out of range (%u materials)", tri_material_host[i], i, nm_eff);
+                return PRT_ERR_INVALID;
+            }
+    }
     float *dv = nullptr, *dn = nullptr;
     uint32_t* dm = nullptr;
     int rc = PRT_OK;
@@ -380,6 +416,7 @@ int prt_get_counters(prt_ctx* ctx, prt_counters* out) {
     out->flagged_rays = c.flagged_rays; out->paths = c.paths;
     out->warp_iters = c.warp_iters; out->node_lane_iters = c.node_lane_iters;
     out->leaf_phases = c.leaf_phases; out->leaf_lane_phases = c.leaf_lane_phases;
+    out->f64_decisions = c.f64_decisions;
     return PRT_OK;
 }
 

@@ -1,9 +1,11 @@
 // traverse.cu -- API-level trace kernels (prt_trace_closest / _any / _all).
 //
-// One ray per thread, 128-thread CTAs, per-thread short stack in shared memory.
-// EXACT launches are followed by resolve_kernel, which re-traces only the rays
-// whose FP32 decisions were within their error bound, in FP64 with the
-// reference's operation order (see traverse.cuh / intersect.cuh).
+// Closest / any hit over the BVH run on the persistent-warp kernel (persist.cuh), in plain FP32 or
+// -- PRT_TRACE_EXACT -- with error bounds: rays whose FP32 decisions were within their bound are
+// appended to a flag list and re-traced by resolve_kernel in FP64 with the reference's operation
+// order (traverse.cuh / intersect.cuh); finalize_kernel gives every unflagged winner the
+// reference's own (t, u, v).  All-hits and brute-force modes use the one-ray-per-thread
+// trace_kernel (parity paths, not timed).
 #include "context.cuh"
 #include "persist.cuh"
 #include "traverse.cuh"
@@ -74,6 +76,8 @@ template <int MODE>
 struct ApiIO {
     const float4* rays;
     void* out;
+    uint32_t* flag_list;       // EXACT only
+    unsigned int* flag_count;
     bool aligned32;  // ray array on a 32-byte boundary (any cudaMalloc'd / torch buffer): one 256-bit load per ray
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         // rays and hits stream through once: evict-first, so they do not push the BVH out of L2
@@ -91,15 +95,52 @@ struct ApiIO {
         else
             reinterpret_cast<uint8_t*>(out)[tag] = gid >= 0 ? 1 : 0;
     }
+    __device__ __forceinline__ void reload(uint32_t tag, float4& ro, float4& rd) const {  // EXACT slow path
+        ro = __ldg(rays + 2ull * tag);
+        rd = __ldg(rays + 2ull * tag + 1);
+    }
+    // EXACT: the ray goes to the FP64 replay; until then its record reads "miss" (finalize_kernel skips it)
+    __device__ __forceinline__ void flag(uint32_t tag) const {
+        flag_list[atomicAdd(flag_count, 1u)] = tag;
+        if (MODE == MODE_CLOSEST) reinterpret_cast<float4*>(out)[tag] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        else reinterpret_cast<uint8_t*>(out)[tag] = 0;
+    }
 };
 
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
+// (gpurun r2-7, soup-1M exact: 8 / 7 / 6 blocks per SM = 64 / 72 / 80 registers -> 9.54 / 10.13 / 10.89 ms)
+#ifndef PRT_MIN_BLOCKS_EXACT
+#define PRT_MIN_BLOCKS_EXACT 8
+#endif
+template <int MODE, bool COUNT, bool EXACT>
+__global__ void __launch_bounds__(kTraceThreads, EXACT ? PRT_MIN_BLOCKS_EXACT : PRT_MIN_BLOCKS)
 trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out,
-                        unsigned int* fetch, Counters* ctr) {
+                        unsigned int* fetch, uint32_t* flag_list, unsigned int* flag_count, Counters* ctr) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
-    ApiIO<MODE> io{rays, out, (reinterpret_cast<uintptr_t>(rays) & 31u) == 0u};
-    trace_persistent<MODE, COUNT>(sc, io, fetch, n, &s_stack[0][threadIdx.x], ctr);
+    ApiIO<MODE> io{rays, out, flag_list, flag_count, (reinterpret_cast<uintptr_t>(rays) & 31u) == 0u};
+    trace_persistent<MODE, COUNT, EXACT>(sc, io, fetch, n, &s_stack[0][threadIdx.x], ctr);
+}
+
+// EXACT closest hit, second pass (fully convergent, one ray per thread): the winner of an unflagged
+// ray is certain, so its (t, u, v) are re-evaluated with the reference's FP64 formula -- t becomes
+// the oracle's t rounded to f32 (the FP32 watertight t degrades for grazing rays).  A winner the
+// FP64 formula rejects (cannot happen within the error bounds; kept as a guard) is flagged.
+__global__ void __launch_bounds__(256)
+finalize_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, float4* hits,
+                uint32_t* flag_list, unsigned int* flag_count) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 h = hits[i];
+    const int gid = __float_as_int(h.w);
+    if (gid < 0) return;
+    const float4 ro = __ldcs(rays + 2ull * i), rd = __ldcs(rays + 2ull * i + 1);
+    const float4* tp = sc.verts_gid + 3ull * gid;
+    const double o[3] = {(double)ro.x, (double)ro.y, (double)ro.z};
+    const double d[3] = {(double)rd.x, (double)rd.y, (double)rd.z};
+    double t, u, v;
+    if (mt_f64(xyz(__ldg(tp)), xyz(__ldg(tp + 1)), xyz(__ldg(tp + 2)), o, d, -1e300, 1e300, t, u, v))
+        hits[i] = make_float4((float)t, (float)u, (float)v, h.w);
+    else
+        flag_list[atomicAdd(flag_count, 1u)] = i;
 }
 
 template <int MODE, bool BRUTE>
@@ -166,26 +207,45 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
         ctx->flag_cap = n;
     }
     if (exact) PRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag_count, 0, sizeof(unsigned int), stream));
-    if (!exact && !brute && mode != MODE_ALL) {
+    if (!brute && mode != MODE_ALL) {
         // one fetch counter per in-flight launch (host-buffer calls pipeline two streams)
         unsigned int* fetch = ctx->fetch_counters + (ctx->fetch_next++ % prt_ctx::kFetchRing);
         PRT_CUDA_TRY(ctx, cudaMemsetAsync(fetch, 0, sizeof(unsigned int), stream));
         if (ctx->grid_persist == 0) {
             int b = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_persistent_kernel<MODE_CLOSEST, false>, kTraceThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_persistent_kernel<MODE_CLOSEST, false, false>, kTraceThreads, 0);
             ctx->grid_persist = ctx->num_sms * (b > 0 ? b : 8);
         }
-        unsigned g = (unsigned)ctx->grid_persist;
+        if (exact && ctx->grid_persist_exact == 0) {
+            int b = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_persistent_kernel<MODE_CLOSEST, false, true>, kTraceThreads, 0);
+            ctx->grid_persist_exact = ctx->num_sms * (b > 0 ? b : 6);
+        }
+        unsigned g = (unsigned)(exact ? ctx->grid_persist_exact : ctx->grid_persist);
         unsigned need = (unsigned)((n + kTraceThreads - 1) / kTraceThreads);
         if (need < g) g = need;
+#define PRT_PERSIST(M, C, E) trace_persistent_kernel<M, C, E><<<g, kTraceThreads, 0, stream>>>( \
+        sc, rays, (unsigned)n, out0, fetch, ctx->flag_list, ctx->flag_count, ctx->counters)
         if (mode == MODE_CLOSEST) {
-            if (count) trace_persistent_kernel<MODE_CLOSEST, true><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
-            else trace_persistent_kernel<MODE_CLOSEST, false><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
+            if (exact) { if (count) PRT_PERSIST(MODE_CLOSEST, true, true); else PRT_PERSIST(MODE_CLOSEST, false, true); }
+            else { if (count) PRT_PERSIST(MODE_CLOSEST, true, false); else PRT_PERSIST(MODE_CLOSEST, false, false); }
         } else {
-            if (count) trace_persistent_kernel<MODE_ANY, true><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
-            else trace_persistent_kernel<MODE_ANY, false><<<g, kTraceThreads, 0, stream>>>(sc, rays, (unsigned)n, out0, fetch, ctx->counters);
+            if (exact) { if (count) PRT_PERSIST(MODE_ANY, true, true); else PRT_PERSIST(MODE_ANY, false, true); }
+            else { if (count) PRT_PERSIST(MODE_ANY, true, false); else PRT_PERSIST(MODE_ANY, false, false); }
         }
+#undef PRT_PERSIST
         PRT_CUDA_TRY(ctx, cudaGetLastError());
+        if (exact) {
+            const unsigned g2 = (unsigned)(ctx->num_sms * 4);
+            if (mode == MODE_CLOSEST) {
+                finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sc, rays, (unsigned)n, (float4*)out0,
+                                                                                ctx->flag_list, ctx->flag_count);
+                resolve_kernel<MODE_CLOSEST, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            } else {
+                resolve_kernel<MODE_ANY, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            }
+            PRT_CUDA_TRY(ctx, cudaGetLastError());
+        }
         return PRT_OK;
     }
     dim3 grid((unsigned)((n + kTraceThreads - 1) / kTraceThreads));

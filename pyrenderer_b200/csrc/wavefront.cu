@@ -171,6 +171,8 @@ struct QueueClosestIO {
     __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
         hits[tag] = make_float4(t, u, v, __int_as_float(gid));
     }
+    __device__ __forceinline__ void flag(uint32_t) const {}  // (EXACT instantiations only)
+    __device__ __forceinline__ void reload(uint32_t, float4&, float4&) const {}
 };
 
 __global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
@@ -178,7 +180,7 @@ closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
                const uint32_t* __restrict__ queue, unsigned int* cnt) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
     QueueClosestIO io{rays, hits, queue};
-    trace_persistent<MODE_CLOSEST, false>(sc, io, cnt + 3, cnt[0], &s_stack[0][threadIdx.x], nullptr);
+    trace_persistent<MODE_CLOSEST, false, false>(sc, io, cnt + 3, cnt[0], &s_stack[0][threadIdx.x], nullptr);
 }
 
 // shadow rays: an unoccluded ray adds its pending NEE contribution to the path's radiance
@@ -206,6 +208,8 @@ struct QueueShadowIO {
             }
         }
     }
+    __device__ __forceinline__ void flag(uint32_t) const {}
+    __device__ __forceinline__ void reload(uint32_t, float4&, float4&) const {}
 };
 
 // LOG: the path-segment log (prt_set_path_log) is a separate instantiation, so the production
@@ -216,7 +220,7 @@ shadow_kernel(SceneDev sc, const __grid_constant__ WaveParams P, const float4* _
               const float4* __restrict__ scontrib, float4* L, unsigned int* cnt) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
     QueueShadowIO<LOG> io{srays, scontrib, L, &P};
-    trace_persistent<MODE_ANY, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
+    trace_persistent<MODE_ANY, false, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
 }
 
 __device__ __forceinline__ float guard_beta(float albedo, float cz, float pdf) {

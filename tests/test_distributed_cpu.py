@@ -36,6 +36,11 @@ def _worker(rank, world, port, out_dir):
     scene, cam = read_file(SCENE_JSON)
     acc = tracing.render_distributed(scene, cam, SPP, max_depth=DEPTH, seed=SEED, render_fn=_oracle_render_fn)
     np.save(os.path.join(out_dir, f"acc{rank}.npy"), acc.numpy())
+    # progressive / resumed call: a PRE-FILLED accumulation buffer gets exactly the new samples added
+    # (an in-place all-reduce of the caller's buffer would multiply what is already there by `world`)
+    more = tracing.render_distributed(scene, cam, 4, max_depth=DEPTH, seed=SEED, render_fn=_oracle_render_fn,
+                                      spp_begin=SPP, accum=acc.clone())
+    np.save(os.path.join(out_dir, f"more{rank}.npy"), more.numpy())
     dist.destroy_process_group()
 
 
@@ -52,3 +57,8 @@ def test_two_rank_sample_sharding_matches_single_rank(tmp_path):
     full = _oracle_render_fn(scene, cam, SPP, DEPTH, SEED, 0, 0xFFFFFFFF, 0, None).numpy()
     assert np.all(a0[..., 3] == SPP)
     assert np.allclose(a0, full, rtol=1e-6, atol=1e-6)
+    m0 = np.load(tmp_path / "more0.npy")
+    assert np.array_equal(m0, np.load(tmp_path / "more1.npy"))
+    full10 = _oracle_render_fn(scene, cam, SPP + 4, DEPTH, SEED, 0, 0xFFFFFFFF, 0, None).numpy()
+    assert np.all(m0[..., 3] == SPP + 4)
+    assert np.allclose(m0, full10, rtol=1e-6, atol=1e-6)

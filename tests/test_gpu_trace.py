@@ -3,9 +3,12 @@
 Contract (BASELINE.json north_star): triangle ids bit-exact against the
 reference's intersection code (here: the oracle, itself bit-exact against the
 reference's numba kernel -- tests/test_oracle_golden.py); t within 4 ulp(f32).
-PRT_TRACE_EXACT is the parity mode: FP32 watertight traversal + FP64 replay of
-the flagged low-margin rays.  The plain FP32 mode is also measured and must
-disagree on at most a tiny, reported fraction of rays.
+PRT_TRACE_EXACT is the parity mode and runs on the SAME persistent-warp kernel
+as the throughput mode (csrc/persist.cuh): FP32 watertight traversal with forward
+error bounds, every low-margin triangle decided in place with the reference's
+FP64 formula, what still cannot be ordered replayed in FP64.  The plain FP32
+mode is also measured and must disagree on at most a tiny, reported fraction of
+rays (thresholds = 3x the measured fraction, gpurun r2-8).
 """
 import numpy as np
 import pytest
@@ -115,7 +118,7 @@ def test_cornell_primary_ids_1024(gpu_ctx, cornell):
     ids_f, _, _, _ = gpu_closest(gpu_ctx, rays, 0)
     frac = np.mean(ids_f != ids_o)
     print(f"[cornell-1024] FP32-only id mismatch fraction {frac:.2e}")
-    assert frac < 1e-3
+    assert frac < 5e-4  # measured 1.74e-4: pixel-centre rays that run exactly along the quads' diagonals
 
 
 def test_cube_obj_primary_ids_1024(gpu_ctx):
@@ -159,7 +162,7 @@ def test_random_soup_bvh_vs_oracle(gpu_ctx, nt, nr, leaf):
     ids_f, _, _, _ = gpu_closest(gpu_ctx, rays, 0)
     frac = np.mean(ids_f != ids_o)
     print(f"[soup{nt}] FP32-only id mismatch fraction {frac:.2e}")
-    assert frac < 1e-3
+    assert frac < 5e-5  # measured 0 on every one of these soups (<= 100k rays)
 
 
 def test_rotations_and_leaf_sizes_do_not_change_hits(gpu_ctx):
@@ -237,7 +240,7 @@ def test_deep_stacks_spill_and_unspill(gpu_ctx):
     ids_f, t_f, _, _ = gpu_closest(gpu_ctx, rays, 0)  # persistent kernel, plain FP32
     frac = np.mean(ids_f != ids_o)
     print(f"[overlap4000] mean hits per ray {cnt_o.mean():.0f}, FP32-only closest id mismatch fraction {frac:.2e}")
-    assert frac < 2e-3
+    assert frac < 5e-4  # measured 1.67e-4 (199 hits per ray: near-ties between overlapping triangles)
     same = ids_f == ids_o
     assert np.abs(t_f[same & (ids_o >= 0)] - t_o[same & (ids_o >= 0)]).max() < 1e-4
 
@@ -371,24 +374,44 @@ def test_host_pipeline_many_chunks_equals_device_call(gpu_ctx):
 
 
 def test_million_triangle_soup_bvh_equals_exhaustive(gpu_ctx):
-    """BASELINE config 4 size (1M triangles): the BVH answer equals the exhaustive GPU
-    answer for every ray (size-independent property), and a CPU-oracle spot check."""
+    """BASELINE config 4 size (1M triangles, the bench scene): the EXACT persistent kernel -- the
+    one bench.py times as `exact` -- equals the CPU oracle on 4096 rays (4e9 reference triangle
+    tests) and the exhaustive GPU answer on 2^14 rays; the plain FP32 throughput kernel (bench
+    `value`) is compared with both at the same size."""
     tris = random_soup(1_000_000, seed=7)
     rays = random_rays(1 << 17, seed=11)
     gpu_ctx.set_triangles(tris)
     st = gpu_ctx.build_bvh()
     print("[soup1M] bvh", st)
     assert st["n_tris"] == 1_000_000 and 0 < st["n_nodes"] < 1_000_000 and st["morton_sorted"] == 1
+    gpu_ctx.reset_counters()
     ids_b, t_b, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+    flagged = gpu_ctx.counters()["flagged_rays"]
     ids_x, t_x, _, _ = gpu_closest(gpu_ctx, rays[: 1 << 14], EXACT | BRUTE)
     assert np.array_equal(ids_b[: 1 << 14], ids_x) and np.array_equal(t_b[: 1 << 14], t_x)
-    ids_o, t_o, _, _ = oracle.closest_hit(tris, rays[:256])
-    assert np.array_equal(ids_b[:256], ids_o)
+    n_o = 4096
+    ids_o, t_o, _, _ = oracle.closest_hit(tris, rays[:n_o])
+    assert np.array_equal(ids_b[:n_o], ids_o)
+    hit = ids_o >= 0
+    assert (np.abs(t_b[:n_o][hit] - t_o[hit]) / t_o[hit]).max() <= 4 * 2.0 ** -23
     assert np.mean(ids_b >= 0) > 0.8
+    # throughput kernel (flags = 0) against the oracle and against the exact kernel
+    ids_f, t_f, _, _ = gpu_closest(gpu_ctx, rays, 0)
+    assert np.sum(ids_f[:n_o] != ids_o) <= 1
+    n_bad = int(np.sum(ids_f != ids_b))
+    print(f"[soup1M] exact: FP64 replays {flagged} of {rays.shape[0]}; plain FP32 vs exact: {n_bad} id mismatches")
+    assert n_bad <= 3  # measured 7.7e-7 of 2^24 rays (profiles/prof_exact.py) -> 0.1 expected in 2^17
     gpu_ctx.reset_counters()
     gpu_closest(gpu_ctx, rays, COUNT)
     c = gpu_ctx.counters()
-    print(f"[soup1M] mean node visits {c['node_visits'] / rays.shape[0]:.1f} tri tests {c['tri_tests'] / rays.shape[0]:.1f}")
+    gpu_ctx.reset_counters()
+    gpu_closest(gpu_ctx, rays, COUNT | EXACT)
+    cx = gpu_ctx.counters()
+    print(f"[soup1M] node visits / tri tests per ray: fp32 {c['node_visits'] / rays.shape[0]:.2f} / {c['tri_tests'] / rays.shape[0]:.2f}, "
+          f"exact {cx['node_visits'] / rays.shape[0]:.2f} / {cx['tri_tests'] / rays.shape[0]:.2f}, "
+          f"in-place FP64 triangle decisions {cx['f64_decisions'] / rays.shape[0]:.2e} per ray")
+    # the error-bound widening must not cost visits (a bound applied to the wrong axis once cost 3 %)
+    assert cx["node_visits"] < 1.01 * c["node_visits"]
 
 
 def test_fuzz_small_scenes_exact_ids(gpu_ctx):
@@ -417,4 +440,5 @@ def test_fuzz_small_scenes_exact_ids(gpu_ctx):
         check_against_oracle(gpu_ctx, tris, rays, EXACT, f"fuzz{nt}/{kind}")
         ids_o = oracle.closest_hit(tris, rays)[0]
         ids_f = gpu_closest(gpu_ctx, rays, 0)[0]
-        assert np.mean(ids_f != ids_o) < 5e-3, f"fuzz{nt}/{kind}: plain FP32 mismatch {np.mean(ids_f != ids_o):.2e}"
+        # measured 0 mismatches on all of them; duplicated triangles tie exactly (lowest id wins in both modes)
+        assert np.sum(ids_f != ids_o) <= 1, f"fuzz{nt}/{kind}: plain FP32 mismatches {np.sum(ids_f != ids_o)} of 1500"

@@ -127,7 +127,7 @@ def test_abi_library_exports_every_declared_symbol():
     assert declared == sorted(_abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.prt_abi_version() == 2
+    assert lib.prt_abi_version() == 3
 
 
 def test_abi_fails_loudly_without_gpu():
