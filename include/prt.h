@@ -110,6 +110,9 @@ typedef struct {
  * compute_brdf_pdf) with the real light area; a path ends on an emitter.  Renders in this mode
  * agree with media/cornell-box/TungstenRender.exr (tests/test_physical.py). */
 #define PRT_RENDER_PHYSICAL 2u
+/* measurement: run the counter-instrumented twins of the traversal kernels, so that prt_get_counters
+ * reports node_visits / tri_tests over the render's own rays (all bounces).  Same image; not timed. */
+#define PRT_RENDER_COUNT 4u
 
 typedef struct {
     uint32_t n_tris, n_nodes, depth, max_leaf_tris;
@@ -237,6 +240,42 @@ int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity,
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
 /* paths per wavefront wave (default 16 Mi = 2.2 GB of path state); 0 keeps the current value */
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths);
+
+/* ---- multi-GPU: sample-sharded render over a replicated scene + BVH (one process per GPU) ----
+ * The reference renders on one device (main.py:28-55, main_taichi.py:80-99); sharding by sample
+ * index is this library's extension (BASELINE.json north_star): rank r of G traces samples
+ * [r*S/G, (r+1)*S/G) of every pixel with its own Philox streams, and ONE all-reduce per frame sums
+ * the fp32 accumulation buffers over NVLink.  NCCL is bound at run time (dlopen of libnccl.so.2 --
+ * inside a PyTorch process that is the copy torch already loaded).
+ *   prt_comm_unique_id   rank 0 makes the 128-byte NCCL id; the caller hands it to every rank
+ *                        (MPI_Bcast, torch.distributed.broadcast, a file ...)
+ *   prt_comm_init        collective: every rank calls it with the same id
+ *   prt_comm_attach      instead: use an ncclComm_t the caller already owns (not destroyed here)
+ *   prt_allreduce_sum    in-place fp32 sum over the ranks, stream-ordered (no-op for one rank)
+ *   prt_render_sharded   one frame: this rank's shard of [spp_begin, spp_end) into a library-owned
+ *                        zeroed buffer, one all-reduce, the sum ADDED to accum_dev (every rank ends
+ *                        with the same buffer) */
+#define PRT_COMM_ID_BYTES 128
+int prt_comm_unique_id(void* id_out);
+int prt_comm_init(prt_ctx* ctx, const void* id, int world, int rank);
+int prt_comm_attach(prt_ctx* ctx, void* nccl_comm, int world, int rank);
+int prt_comm_destroy(prt_ctx* ctx);
+int prt_comm_info(const prt_ctx* ctx, int* world, int* rank, int* nccl_version);
+int prt_allreduce_sum(prt_ctx* ctx, float* buf_dev, uint64_t n_floats, void* stream);
+int prt_render_sharded(prt_ctx* ctx, const prt_render_params* params, float* accum_dev, void* stream);
+
+/* ---- device time per kernel class (measurement aid; bench.py's roofline lines use it) ----
+ * Between prt_profile_begin and prt_profile_end every kernel launch of this context is bracketed
+ * by a cudaEvent pair on the launching stream; _end synchronises the device and returns the sums. */
+enum { PRT_PROF_RAYGEN = 0, PRT_PROF_CLOSEST = 1, PRT_PROF_SHADE = 2, PRT_PROF_SHADOW = 3,
+       PRT_PROF_EXACT_FIXUP = 4 /* finalize + FP64 replay of PRT_TRACE_EXACT */, PRT_PROF_OTHER = 5,
+       PRT_PROF_ALLREDUCE = 6, PRT_PROF_CLASSES = 8 };
+typedef struct {
+    float ms[PRT_PROF_CLASSES];
+    uint32_t launches[PRT_PROF_CLASSES];
+} prt_kernel_times;
+int prt_profile_begin(prt_ctx* ctx);
+int prt_profile_end(prt_ctx* ctx, prt_kernel_times* out); /* synchronous */
 
 int prt_get_counters(prt_ctx* ctx, prt_counters* out); /* synchronous */
 int prt_reset_counters(prt_ctx* ctx);

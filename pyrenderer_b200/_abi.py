@@ -23,6 +23,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE = 1, 2, 4
 RENDER_EXACT_PRIMARY = 1
 RENDER_PHYSICAL = 2
+RENDER_COUNT = 4
 
 
 class PrtCamera(C.Structure):
@@ -58,12 +59,20 @@ class PrtCounters(C.Structure):
                 ("leaf_lane_phases", C.c_uint64), ("f64_decisions", C.c_uint64)]
 
 
+class PrtKernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_float * 8), ("launches", C.c_uint32 * 8)]
+
+
+PROF_CLASSES = ("raygen", "closest", "shade", "shadow", "exact_fixup", "other", "allreduce")
+COMM_ID_BYTES = 128
+
 EXPORTS = [
     "prt_abi_version", "prt_create", "prt_destroy", "prt_last_error", "prt_scene_set_triangles",
     "prt_scene_set_triangles_dev", "prt_bvh_build", "prt_camera_set", "prt_generate_rays",
     "prt_trace_closest", "prt_trace_any", "prt_trace_all", "prt_trace_closest_host", "prt_render", "prt_trace_paths",
     "prt_render_host", "prt_set_wave_paths", "prt_set_path_log", "prt_get_counters", "prt_reset_counters",
-    "prt_synchronize",
+    "prt_synchronize", "prt_comm_unique_id", "prt_comm_init", "prt_comm_attach", "prt_comm_destroy", "prt_comm_info",
+    "prt_allreduce_sum", "prt_render_sharded", "prt_profile_begin", "prt_profile_end",
 ]
 
 
@@ -106,6 +115,15 @@ def load():
     lib.prt_get_counters.argtypes = [vp, C.POINTER(PrtCounters)]
     lib.prt_reset_counters.argtypes = [vp]
     lib.prt_synchronize.argtypes = [vp]
+    lib.prt_comm_unique_id.argtypes = [vp]
+    lib.prt_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.prt_comm_attach.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.prt_comm_destroy.argtypes = [vp]
+    lib.prt_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.prt_allreduce_sum.argtypes = [vp, vp, u64, vp]
+    lib.prt_render_sharded.argtypes = [vp, C.POINTER(PrtRenderParams), vp, vp]
+    lib.prt_profile_begin.argtypes = [vp]
+    lib.prt_profile_end.argtypes = [vp, C.POINTER(PrtKernelTimes)]
     for name in EXPORTS:
         if name not in ("prt_destroy", "prt_last_error"):
             getattr(lib, name).restype = C.c_int
@@ -266,6 +284,47 @@ class Context:
 
     def set_wave_paths(self, paths):
         self._check(self.lib.prt_set_wave_paths(self.h, int(paths)))
+
+    # -- multi-GPU ------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (rank 0 makes it; hand it to every rank)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load().prt_comm_unique_id(buf)
+        if rc != 0:
+            raise PrtError(f"[{rc}] prt_comm_unique_id failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, uid, world, rank):
+        assert len(uid) == COMM_ID_BYTES
+        self._check(self.lib.prt_comm_init(self.h, C.c_char_p(uid), int(world), int(rank)))
+
+    def comm_destroy(self):
+        self._check(self.lib.prt_comm_destroy(self.h))
+
+    def comm_info(self):
+        w, r, v = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.prt_comm_info(self.h, C.byref(w), C.byref(r), C.byref(v)))
+        return {"world": w.value, "rank": r.value, "nccl_version": v.value}
+
+    def allreduce_sum(self, buf_dev, n_floats=None, stream=None):
+        n = int(buf_dev.numel()) if n_floats is None else int(n_floats)
+        self._check(self.lib.prt_allreduce_sum(self.h, _dev_ptr(buf_dev), n, _stream_ptr(stream, self.device)))
+
+    def render_sharded(self, params, accum_dev, stream=None):
+        """One frame of the sample-sharded render: this rank's shard, one all-reduce, sum added to accum."""
+        self._check(self.lib.prt_render_sharded(self.h, C.byref(params), _dev_ptr(accum_dev),
+                                                _stream_ptr(stream, self.device)))
+
+    # -- measurement ----------------------------------------------------------
+    def profile_begin(self):
+        self._check(self.lib.prt_profile_begin(self.h))
+
+    def profile_end(self):
+        """{class: (ms, launches)} of every kernel launched since profile_begin (synchronises)."""
+        t = PrtKernelTimes()
+        self._check(self.lib.prt_profile_end(self.h, C.byref(t)))
+        return {name: (float(t.ms[i]), int(t.launches[i])) for i, name in enumerate(PROF_CLASSES)}
 
     def counters(self):
         c = PrtCounters()

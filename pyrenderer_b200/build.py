@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libprt.so")
-SOURCES = ["prt_api.cu", "traverse.cu", "bvh_build.cu", "wavefront.cu"]
+SOURCES = ["prt_api.cu", "traverse.cu", "bvh_build.cu", "wavefront.cu", "collective.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -60,7 +60,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}")
             objs.append(obj)
-    cmd = [exe, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [exe, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

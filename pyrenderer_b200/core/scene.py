@@ -23,6 +23,14 @@ class Scene:
         self._ctx = None
         self._arrays = None
 
+    @classmethod
+    def from_arrays(cls, arrays):
+        """Scene over ready-made flat arrays (the dict :meth:`arrays` returns), e.g. a subdivided or
+        procedurally generated mesh; the primitive list stays empty."""
+        s = cls()
+        s._arrays = dict(arrays)
+        return s
+
     # -- reference protocol -------------------------------------------------
     def add_primitive(self, prim):
         prim.id = len(self.primitives)

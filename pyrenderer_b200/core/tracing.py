@@ -112,6 +112,24 @@ def default_device():
     return torch.cuda.current_device() if torch.cuda.is_available() else 0
 
 
+def init_distributed(scene, device=None, group=None):
+    """Give the scene's device context an NCCL communicator over the ranks of the torch.distributed
+    ``group`` (C ABI: prt_comm_unique_id on rank 0, the 128 bytes broadcast through the group,
+    prt_comm_init on every rank).  After this, :func:`render_distributed` runs the whole frame --
+    shard render, all-reduce, accumulate -- inside libprt.so (prt_render_sharded)."""
+    import torch.distributed as dist
+    if device is None:
+        device = default_device()
+    ctx = scene.commit(device)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if ctx.comm_info()["world"] == world and world > 1:
+        return ctx
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(box[0], world, rank)
+    return ctx
+
+
 def render_distributed(scene, camera, spp, max_depth=5, seed=1, rr_start=RR_OFF, device=None,
                        accum=None, group=None, render_fn=None, spp_begin=0, **render_kw):
     """Samples [spp_begin, spp_begin+spp) of every pixel, sharded over the ranks of ``group``
@@ -129,6 +147,21 @@ def render_distributed(scene, camera, spp, max_depth=5, seed=1, rr_start=RR_OFF,
     world = dist.get_world_size(group) if on else 1
     if device is None:
         device = default_device()
+    if render_fn is None and world == 1:  # one rank: the plain frame, still ONE C-ABI call
+        return render(scene, camera, spp=spp, max_depth=max_depth, seed=seed, spp_begin=spp_begin,
+                      rr_start=rr_start, device=device, accum=accum, **render_kw)
+    if render_fn is None and world > 1:
+        ctx = scene.commit(device)
+        if ctx.comm_info()["world"] == world:  # init_distributed was called: the C-ABI frame
+            ctx.set_camera(*camera.device_record(), aperture=float(getattr(camera, "aperture", 0.0)))
+            if accum is None:
+                accum = new_accum(camera, device)
+            flags = (1 if render_kw.get("exact_primary", True) else 0) | (2 if render_kw.get("physical", False) else 0)
+            params = ctx.render_params(seed=seed, spp_begin=spp_begin, spp_end=spp_begin + spp, max_depth=max_depth,
+                                       rr_start=rr_start, light_color=render_kw.get("light_color", LIGHT_COLOR),
+                                       tmin=T_MIN, tmax=T_MAX, flags=flags)
+            ctx.render_sharded(params, accum, render_kw.get("stream"))
+            return accum
     s0, s1 = shard_samples(spp, rank, world)
     shard = (render_fn or render)(scene, camera, spp=s1 - s0, max_depth=max_depth, seed=seed,
                                   spp_begin=spp_begin + s0, rr_start=rr_start, device=device, accum=None,

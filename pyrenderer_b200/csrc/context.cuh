@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -31,11 +32,14 @@ struct prt_ctx {
     prt_camera cam = {};
     bool cam_set = false;
 
-    // counters + exact-mode scratch
+    // counters + exact-mode scratch: one (flag list, flag count) pair per in-flight EXACT launch,
+    // so that the host-buffer pipeline can keep two exact traces on two streams
     prt::Counters* counters = nullptr;  // device
-    uint32_t* flag_list = nullptr;
-    unsigned int* flag_count = nullptr;
-    uint64_t flag_cap = 0;
+    static constexpr unsigned kFlagRing = 4;
+    uint32_t* flag_list[kFlagRing] = {};
+    unsigned int* flag_count = nullptr;  // [kFlagRing]
+    uint64_t flag_cap[kFlagRing] = {};
+    unsigned flag_next = 0;
     static constexpr unsigned kFetchRing = 32;
     unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
     unsigned fetch_next = 0;
@@ -53,6 +57,19 @@ struct prt_ctx {
     // wavefront state (wavefront.cu)
     void* wf = nullptr;
     uint64_t wave_paths = 16ull << 20;
+    // multi-GPU (collective.cu): communicator, this rank, and the per-frame shard buffer
+    void* comm = nullptr;  // ncclComm_t
+    bool comm_owned = false;
+    int comm_world = 1, comm_rank = 0;
+    float* shard_accum = nullptr;
+    size_t shard_bytes = 0;
+
+    // per-kernel-class timing (prt_profile_begin / _end): event pairs on the launching stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;  // pool; pair i = events 2i, 2i+1
+    std::vector<int> prof_class;           // class of pair i
+    std::vector<int> prof_launches;        // kernel launches inside pair i
+
     // path-segment log (prt_set_path_log); caller-owned device memory
     float4* log_segments = nullptr;
     uint32_t* log_count = nullptr;
@@ -87,6 +104,12 @@ struct prt_ctx {
 };
 
 namespace prt {
+// kernel classes of prt_kernel_times (include/prt.h PRT_PROF_*)
+enum { PROF_RAYGEN = 0, PROF_CLOSEST = 1, PROF_SHADE = 2, PROF_SHADOW = 3, PROF_EXACT_FIXUP = 4, PROF_OTHER = 5,
+       PROF_ALLREDUCE = 6, PROF_N = 8 };
+// prt_api.cu: bracket the next `launches` kernel launches on `stream` (no-ops unless profiling is on)
+void prof_begin(prt_ctx* ctx, int cls, cudaStream_t stream, int launches = 1);
+void prof_end(prt_ctx* ctx, cudaStream_t stream);
 // traverse.cu
 int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* out0, void* out1,
                  uint32_t flags, cudaStream_t stream);

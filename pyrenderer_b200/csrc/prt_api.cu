@@ -94,6 +94,24 @@ static int set_scene_common(prt_ctx* ctx, const float* verts_dev, const float* n
     return PRT_OK;
 }
 
+void prof_begin(prt_ctx* ctx, int cls, cudaStream_t stream, int launches) {
+    if (!ctx->prof_on) return;
+    const size_t i = ctx->prof_class.size();
+    while (ctx->prof_events.size() < 2 * (i + 1)) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) { ctx->prof_on = false; return; }
+        ctx->prof_events.push_back(e);
+    }
+    ctx->prof_class.push_back(cls);
+    ctx->prof_launches.push_back(launches);
+    cudaEventRecord(ctx->prof_events[2 * i], stream);
+}
+
+void prof_end(prt_ctx* ctx, cudaStream_t stream) {
+    if (!ctx->prof_on || ctx->prof_class.empty()) return;
+    cudaEventRecord(ctx->prof_events[2 * (ctx->prof_class.size() - 1) + 1], stream);
+}
+
 }  // namespace prt
 
 using namespace prt;
@@ -154,7 +172,7 @@ int prt_create(int device, prt_ctx** out) {
     }
     if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(Counters));
     if (e == cudaSuccess) e = cudaMemset(c->counters, 0, sizeof(Counters));
-    if (e == cudaSuccess) e = cudaMalloc(&c->flag_count, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->flag_count, sizeof(unsigned int) * prt_ctx::kFlagRing);
     if (e == cudaSuccess) e = cudaMalloc(&c->fetch_counters, sizeof(unsigned int) * prt_ctx::kFetchRing);
     if (e != cudaSuccess) {
         snprintf(g_create_error, sizeof g_create_error, "prt_create: %s", cudaGetErrorString(e));
@@ -169,9 +187,13 @@ void prt_destroy(prt_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard;
     guard.enter(ctx->device);
+    prt_comm_destroy(ctx);
     wavefront_free(ctx);
     free_scene(ctx);
-    cudaFree(ctx->counters); cudaFree(ctx->flag_list); cudaFree(ctx->flag_count);
+    cudaFree(ctx->shard_accum);
+    for (auto& e : ctx->prof_events) cudaEventDestroy(e);
+    for (auto& l : ctx->flag_list) cudaFree(l);
+    cudaFree(ctx->counters); cudaFree(ctx->flag_count);
     cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]); cudaFree(ctx->fetch_counters);
     for (auto& s : ctx->copy_stream) if (s) cudaStreamDestroy(s);
     for (auto& e : ctx->copy_event) if (e) cudaEventDestroy(e);
@@ -298,7 +320,8 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
     // of chunk i+1.., the trace of chunk i and the download of chunk i-1 overlap, each copy engine
     // sees a FIFO, and because consecutive traces sit on different streams the CTAs of chunk i+1
     // move into the SM slots that the draining tail of chunk i frees (a persistent launch ends with
-    // a few long rays on mostly idle SMs).  EXACT launches share one flag list: one trace stream.
+    // a few long rays on mostly idle SMs).  EXACT launches take their flag lists from a ring of
+    // prt_ctx::kFlagRing, so they pipeline the same way.
     constexpr int S = prt_ctx::kHostSlots;
     const uint64_t chunk = 1ull << 21;
     const uint64_t cap = n < S * chunk ? n : S * chunk;
@@ -312,11 +335,10 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
     prt_ray* dr = (prt_ray*)ctx->stage[0];
     prt_hit* dh = (prt_hit*)ctx->stage[1];
     cudaStream_t s_up = ctx->copy_stream[0], s_down = ctx->copy_stream[2];
-    const bool one_trace_stream = (flags & PRT_TRACE_EXACT) != 0;
     uint64_t done = 0;
     for (uint64_t i = 0; done < n; ++i) {
         const int slot = (int)(i % S);
-        cudaStream_t s_tr = ctx->copy_stream[(one_trace_stream || (i & 1) == 0) ? 1 : 3];
+        cudaStream_t s_tr = ctx->copy_stream[(i & 1) == 0 ? 1 : 3];
         cudaEvent_t uploaded = ctx->copy_event[3 * slot], traced = ctx->copy_event[3 * slot + 1],
                     downloaded = ctx->copy_event[3 * slot + 2];
         const uint64_t m = n - done < chunk ? n - done : chunk;
@@ -401,6 +423,33 @@ int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity,
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths) {
     CHECK_CTX(ctx);
     if (paths) ctx->wave_paths = paths;
+    return PRT_OK;
+}
+
+int prt_profile_begin(prt_ctx* ctx) {
+    CHECK_CTX(ctx);
+    ctx->prof_class.clear();
+    ctx->prof_launches.clear();
+    ctx->prof_on = true;
+    return PRT_OK;
+}
+
+int prt_profile_end(prt_ctx* ctx, prt_kernel_times* out) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (!out) { ctx->set_error("profile_end: out == NULL"); return PRT_ERR_INVALID; }
+    ctx->prof_on = false;
+    memset(out, 0, sizeof *out);
+    PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    for (size_t i = 0; i < ctx->prof_class.size(); ++i) {
+        float ms = 0.f;
+        PRT_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+        const int c = ctx->prof_class[i];
+        out->ms[c] += ms;
+        out->launches[c] += (uint32_t)ctx->prof_launches[i];
+    }
+    ctx->prof_class.clear();
+    ctx->prof_launches.clear();
     return PRT_OK;
 }
 

@@ -200,13 +200,21 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
     if (!ctx->scene_set) { ctx->set_error("trace: no scene (call prt_scene_set_triangles first)"); return PRT_ERR_STATE; }
     if (!brute && !ctx->bvh_built) { ctx->set_error("trace: BVH not built (call prt_bvh_build or pass PRT_TRACE_BRUTE)"); return PRT_ERR_STATE; }
     SceneDev sc = ctx->scene_dev();
-    if (exact && ctx->flag_cap < n) {
-        if (ctx->flag_list) cudaFree(ctx->flag_list);
-        ctx->flag_list = nullptr; ctx->flag_cap = 0;
-        PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->flag_list, n * sizeof(uint32_t)));
-        ctx->flag_cap = n;
+    uint32_t* flag_list = nullptr;
+    unsigned int* flag_count = nullptr;
+    if (exact) {  // grow-only flag list of this launch's ring slot (worst case: every ray flagged)
+        const unsigned slot = ctx->flag_next++ % prt_ctx::kFlagRing;
+        if (ctx->flag_cap[slot] < n) {
+            PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());  // an earlier launch (any stream) may still use the old list
+            cudaFree(ctx->flag_list[slot]);
+            ctx->flag_list[slot] = nullptr; ctx->flag_cap[slot] = 0;
+            PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->flag_list[slot], n * sizeof(uint32_t)));
+            ctx->flag_cap[slot] = n;
+        }
+        flag_list = ctx->flag_list[slot];
+        flag_count = ctx->flag_count + slot;
+        PRT_CUDA_TRY(ctx, cudaMemsetAsync(flag_count, 0, sizeof(unsigned int), stream));
     }
-    if (exact) PRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag_count, 0, sizeof(unsigned int), stream));
     if (!brute && mode != MODE_ALL) {
         // one fetch counter per in-flight launch (host-buffer calls pipeline two streams)
         unsigned int* fetch = ctx->fetch_counters + (ctx->fetch_next++ % prt_ctx::kFetchRing);
@@ -224,8 +232,9 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
         unsigned g = (unsigned)(exact ? ctx->grid_persist_exact : ctx->grid_persist);
         unsigned need = (unsigned)((n + kTraceThreads - 1) / kTraceThreads);
         if (need < g) g = need;
+        prof_begin(ctx, mode == MODE_CLOSEST ? PROF_CLOSEST : PROF_SHADOW, stream);
 #define PRT_PERSIST(M, C, E) trace_persistent_kernel<M, C, E><<<g, kTraceThreads, 0, stream>>>( \
-        sc, rays, (unsigned)n, out0, fetch, ctx->flag_list, ctx->flag_count, ctx->counters)
+        sc, rays, (unsigned)n, out0, fetch, flag_list, flag_count, ctx->counters)
         if (mode == MODE_CLOSEST) {
             if (exact) { if (count) PRT_PERSIST(MODE_CLOSEST, true, true); else PRT_PERSIST(MODE_CLOSEST, false, true); }
             else { if (count) PRT_PERSIST(MODE_CLOSEST, true, false); else PRT_PERSIST(MODE_CLOSEST, false, false); }
@@ -234,38 +243,41 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
             else { if (count) PRT_PERSIST(MODE_ANY, true, false); else PRT_PERSIST(MODE_ANY, false, false); }
         }
 #undef PRT_PERSIST
+        prof_end(ctx, stream);
         PRT_CUDA_TRY(ctx, cudaGetLastError());
         if (exact) {
             const unsigned g2 = (unsigned)(ctx->num_sms * 4);
+            prof_begin(ctx, PROF_EXACT_FIXUP, stream, mode == MODE_CLOSEST ? 2 : 1);
             if (mode == MODE_CLOSEST) {
                 finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sc, rays, (unsigned)n, (float4*)out0,
-                                                                                ctx->flag_list, ctx->flag_count);
-                resolve_kernel<MODE_CLOSEST, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+                                                                                flag_list, flag_count);
+                resolve_kernel<MODE_CLOSEST, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
             } else {
-                resolve_kernel<MODE_ANY, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+                resolve_kernel<MODE_ANY, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
             }
+            prof_end(ctx, stream);
             PRT_CUDA_TRY(ctx, cudaGetLastError());
         }
         return PRT_OK;
     }
     dim3 grid((unsigned)((n + kTraceThreads - 1) / kTraceThreads));
     switch (mode) {
-        case MODE_CLOSEST: launch1<MODE_CLOSEST>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;
-        case MODE_ANY: launch1<MODE_ANY>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;
-        default: launch1<MODE_ALL>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters); break;
+        case MODE_CLOSEST: launch1<MODE_CLOSEST>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, flag_list, flag_count, ctx->counters); break;
+        case MODE_ANY: launch1<MODE_ANY>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, flag_list, flag_count, ctx->counters); break;
+        default: launch1<MODE_ALL>(exact, count, brute, grid, stream, sc, rays, n, out0, out1, flag_list, flag_count, ctx->counters); break;
     }
     PRT_CUDA_TRY(ctx, cudaGetLastError());
     if (exact) {
         dim3 g2((unsigned)(ctx->num_sms * 4));
         if (mode == MODE_CLOSEST) {
-            if (brute) resolve_kernel<MODE_CLOSEST, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
-            else resolve_kernel<MODE_CLOSEST, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            if (brute) resolve_kernel<MODE_CLOSEST, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
+            else resolve_kernel<MODE_CLOSEST, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
         } else if (mode == MODE_ANY) {
-            if (brute) resolve_kernel<MODE_ANY, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
-            else resolve_kernel<MODE_ANY, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            if (brute) resolve_kernel<MODE_ANY, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
+            else resolve_kernel<MODE_ANY, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
         } else {
-            if (brute) resolve_kernel<MODE_ALL, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
-            else resolve_kernel<MODE_ALL, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, ctx->flag_list, ctx->flag_count, ctx->counters);
+            if (brute) resolve_kernel<MODE_ALL, true><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
+            else resolve_kernel<MODE_ALL, false><<<g2, kTraceThreads, 0, stream>>>(sc, rays, out0, out1, flag_list, flag_count, ctx->counters);
         }
         PRT_CUDA_TRY(ctx, cudaGetLastError());
     }

@@ -175,12 +175,15 @@ struct QueueClosestIO {
     __device__ __forceinline__ void reload(uint32_t, float4&, float4&) const {}
 };
 
+// COUNT (PRT_RENDER_COUNT): the counter-instrumented twin -- node visits / triangle tests per ray of
+// the render's own ray population (all bounces), for the render leg's roofline; never timed
+template <bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 closest_kernel(SceneDev sc, const float4* __restrict__ rays, float4* hits,
-               const uint32_t* __restrict__ queue, unsigned int* cnt) {
+               const uint32_t* __restrict__ queue, unsigned int* cnt, Counters* ctr) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
     QueueClosestIO io{rays, hits, queue};
-    trace_persistent<MODE_CLOSEST, false, false>(sc, io, cnt + 3, cnt[0], &s_stack[0][threadIdx.x], nullptr);
+    trace_persistent<MODE_CLOSEST, COUNT, false>(sc, io, cnt + 3, cnt[0], &s_stack[0][threadIdx.x], ctr);
 }
 
 // shadow rays: an unoccluded ray adds its pending NEE contribution to the path's radiance
@@ -214,13 +217,13 @@ struct QueueShadowIO {
 
 // LOG: the path-segment log (prt_set_path_log) is a separate instantiation, so the production
 // kernels carry none of it (as a run-time flag it cost the Cornell render 9 %)
-template <bool LOG>
+template <bool LOG, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads, PRT_MIN_BLOCKS)
 shadow_kernel(SceneDev sc, const __grid_constant__ WaveParams P, const float4* __restrict__ srays,
-              const float4* __restrict__ scontrib, float4* L, unsigned int* cnt) {
+              const float4* __restrict__ scontrib, float4* L, unsigned int* cnt, Counters* ctr) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
     QueueShadowIO<LOG> io{srays, scontrib, L, &P};
-    trace_persistent<MODE_ANY, false, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], nullptr);
+    trace_persistent<MODE_ANY, COUNT, false>(sc, io, cnt + 4, cnt[2], &s_stack[0][threadIdx.x], ctr);
 }
 
 __device__ __forceinline__ float guard_beta(float albedo, float cz, float pdf) {
@@ -439,9 +442,12 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
     }
 }
 
-__global__ void advance_kernel(unsigned int* cnt, Counters* ctr) {
-    atomicAdd(&ctr->rays_closest, (unsigned long long)cnt[0]);
-    atomicAdd(&ctr->rays_shadow, (unsigned long long)cnt[2]);
+// (count_rays = false under PRT_RENDER_COUNT: the counted traversal kernels add the rays themselves)
+__global__ void advance_kernel(unsigned int* cnt, Counters* ctr, bool count_rays) {
+    if (count_rays) {
+        atomicAdd(&ctr->rays_closest, (unsigned long long)cnt[0]);
+        atomicAdd(&ctr->rays_shadow, (unsigned long long)cnt[2]);
+    }
     cnt[0] = cnt[1];
     cnt[1] = 0; cnt[2] = 0; cnt[3] = 0; cnt[4] = 0;
 }
@@ -506,7 +512,7 @@ static int wave_alloc(prt_ctx* ctx, uint64_t cap) {
     PRT_CUDA_TRY(ctx, cudaMalloc(&w->cnt, sizeof(unsigned int) * 8));
     w->cap = cap;
     int bt = 0, bs = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, closest_kernel, kTraceThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, closest_kernel<false>, kTraceThreads, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, shade_kernel<false, false>, 256, 0);
     w->grid_trace = ctx->num_sms * (bt > 0 ? bt : 4);
     w->grid_shade = ctx->num_sms * (bs > 0 ? bs : 4);
@@ -541,31 +547,47 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
         P.s_begin = s;
         P.ns_wave = (uint32_t)((p->spp_end - s) < per_wave ? (p->spp_end - s) : per_wave);
         uint32_t n_paths = P.npix * P.ns_wave;
+        prof_begin(ctx, PROF_RAYGEN, stream);
         if (user_rays)
             init_paths_kernel<<<(n_paths + 255) / 256, 256, 0, stream>>>(user_rays, P, w->rays, w->beta, w->L, w->queue[0], w->cnt);
         else
             raygen_kernel<<<(n_paths + 255) / 256, 256, 0, stream>>>(cam, P, w->rays, w->beta, w->L, w->queue[0], w->cnt);
+        prof_end(ctx, stream);
+        const bool counted = (p->flags & PRT_RENDER_COUNT) != 0;
         for (uint32_t b = 0; b < p->max_depth; ++b) {
             uint32_t* qin = w->queue[b & 1];
             uint32_t* qout = w->queue[(b & 1) ^ 1];
             if (b == 0 && (p->flags & PRT_RENDER_EXACT_PRIMARY)) {
                 // bounce 0: queue == identity, rays contiguous -> the API-level exact trace applies
-                rc = launch_trace(ctx, MODE_CLOSEST, w->rays, n_paths, w->hits, nullptr, PRT_TRACE_EXACT, stream);
+                rc = launch_trace(ctx, MODE_CLOSEST, w->rays, n_paths, w->hits, nullptr,
+                                  PRT_TRACE_EXACT | (counted ? PRT_TRACE_COUNT : 0u), stream);
                 if (rc != PRT_OK) return rc;
             } else {
-                closest_kernel<<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt);
+                prof_begin(ctx, PROF_CLOSEST, stream);
+                if (counted) closest_kernel<true><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt, ctx->counters);
+                else closest_kernel<false><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, w->rays, w->hits, qin, w->cnt, ctx->counters);
+                prof_end(ctx, stream);
             }
             const bool phys = p->flags & PRT_RENDER_PHYSICAL, logging = P.log != nullptr;
 #define PRT_SHADE(PH, LG) shade_kernel<PH, LG><<<w->grid_shade, 256, 0, stream>>>(sc, P, b, p->max_depth, w->rays, w->hits, \
                                                   w->beta, w->L, w->srays, w->scontrib, qin, qout, w->cnt, prim_ids)
+            prof_begin(ctx, PROF_SHADE, stream);
             if (logging) { if (phys) PRT_SHADE(true, true); else PRT_SHADE(false, true); }
             else { if (phys) PRT_SHADE(true, false); else PRT_SHADE(false, false); }
 #undef PRT_SHADE
-            if (logging) shadow_kernel<true><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt);
-            else shadow_kernel<false><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt);
-            advance_kernel<<<1, 1, 0, stream>>>(w->cnt, ctx->counters);
+            prof_end(ctx, stream);
+            prof_begin(ctx, PROF_SHADOW, stream);
+            if (logging) shadow_kernel<true, false><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt, ctx->counters);
+            else if (counted) shadow_kernel<false, true><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt, ctx->counters);
+            else shadow_kernel<false, false><<<w->grid_trace, kTraceThreads, 0, stream>>>(sc, P, w->srays, w->scontrib, w->L, w->cnt, ctx->counters);
+            prof_end(ctx, stream);
+            prof_begin(ctx, PROF_OTHER, stream);
+            advance_kernel<<<1, 1, 0, stream>>>(w->cnt, ctx->counters, !counted);
+            prof_end(ctx, stream);
         }
+        prof_begin(ctx, PROF_OTHER, stream);
         accumulate_kernel<<<(P.npix + 255) / 256, 256, 0, stream>>>(w->L, P.npix, P.ns_wave, (float4*)accum, ctx->counters);
+        prof_end(ctx, stream);
     }
     PRT_CUDA_TRY(ctx, cudaGetLastError());
     return PRT_OK;
