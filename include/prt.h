@@ -118,7 +118,9 @@ typedef struct {
     uint32_t n_tris, n_nodes, depth, max_leaf_tris;
     uint32_t morton_sorted; /* 1 if the radix sort left the Morton keys in order (self-check) */
     float sah_cost;
-    float ms_total, ms_morton, ms_sort, ms_hierarchy, ms_refit, ms_emit;
+    float ms_total, ms_morton, ms_sort, ms_hierarchy, ms_refit, ms_emit; /* device time per phase (events) */
+    float ms_wall;        /* host wall clock of the whole prt_bvh_build call: triangle buffer in -> traversable BVH */
+    uint32_t morton_bits; /* 30 or 63: key width this build used */
 } prt_bvh_stats;
 
 typedef struct {
@@ -154,6 +156,8 @@ typedef struct {
     uint32_t rotations;     /* number of bottom-up SAH rotation passes during refit (0 = none, default 1) */
     uint32_t treelets;      /* 1 (default): every maximal subtree of <= 128 triangles of the Morton
                                hierarchy is rebuilt with binned SAH before refit; 0 = plain LBVH */
+    uint32_t morton_bits;   /* 30, 63, or 0 (default) = 30 unless more than 1/16 of the sorted neighbours
+                               share a 30-bit cell (clustered geometry), then 63 (21 bits per axis) */
 } prt_bvh_options;
 
 int prt_abi_version(void);
@@ -238,6 +242,11 @@ typedef struct {
 int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity, uint32_t* count_dev);
 /* same with a HOST accumulation buffer (upload, render, download; synchronous) */
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
+/* Device memory is grow-only: scene, BVH, build scratch, staging and wavefront buffers are kept and
+ * reused by later calls (a rebuild or a new scene of the same size allocates nothing).  This frees
+ * everything that is scratch (build arena, host-call staging, exact-mode flag lists, wavefront
+ * state); the scene and its BVH stay usable. */
+int prt_release_scratch(prt_ctx* ctx);
 /* paths per wavefront wave (default 16 Mi = 2.2 GB of path state); 0 keeps the current value */
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths);
 

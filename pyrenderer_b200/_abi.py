@@ -43,12 +43,12 @@ class PrtBvhStats(C.Structure):
     _fields_ = [("n_tris", C.c_uint32), ("n_nodes", C.c_uint32), ("depth", C.c_uint32),
                 ("max_leaf_tris", C.c_uint32), ("morton_sorted", C.c_uint32), ("sah_cost", C.c_float), ("ms_total", C.c_float),
                 ("ms_morton", C.c_float), ("ms_sort", C.c_float), ("ms_hierarchy", C.c_float),
-                ("ms_refit", C.c_float), ("ms_emit", C.c_float)]
+                ("ms_refit", C.c_float), ("ms_emit", C.c_float), ("ms_wall", C.c_float), ("morton_bits", C.c_uint32)]
 
 
 class PrtBvhOptions(C.Structure):
     _fields_ = [("max_leaf_tris", C.c_uint32), ("cost_node", C.c_float), ("cost_tri", C.c_float),
-                ("rotations", C.c_uint32), ("treelets", C.c_uint32)]
+                ("rotations", C.c_uint32), ("treelets", C.c_uint32), ("morton_bits", C.c_uint32)]
 
 
 class PrtCounters(C.Structure):
@@ -72,7 +72,7 @@ EXPORTS = [
     "prt_trace_closest", "prt_trace_any", "prt_trace_all", "prt_trace_closest_host", "prt_render", "prt_trace_paths",
     "prt_render_host", "prt_set_wave_paths", "prt_set_path_log", "prt_get_counters", "prt_reset_counters",
     "prt_synchronize", "prt_comm_unique_id", "prt_comm_init", "prt_comm_attach", "prt_comm_destroy", "prt_comm_info",
-    "prt_allreduce_sum", "prt_render_sharded", "prt_profile_begin", "prt_profile_end",
+    "prt_allreduce_sum", "prt_render_sharded", "prt_profile_begin", "prt_profile_end", "prt_release_scratch",
 ]
 
 
@@ -122,6 +122,7 @@ def load():
     lib.prt_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.prt_allreduce_sum.argtypes = [vp, vp, u64, vp]
     lib.prt_render_sharded.argtypes = [vp, C.POINTER(PrtRenderParams), vp, vp]
+    lib.prt_release_scratch.argtypes = [vp]
     lib.prt_profile_begin.argtypes = [vp]
     lib.prt_profile_end.argtypes = [vp, C.POINTER(PrtKernelTimes)]
     for name in EXPORTS:
@@ -200,8 +201,9 @@ class Context:
         self._check(self.lib.prt_scene_set_triangles_dev(self.h, _dev_ptr(verts_dev), int(nt),
                                                          _stream_ptr(stream, self.device)))
 
-    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=2.0, rotations=1, treelets=1):
-        opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations), int(treelets))
+    def build_bvh(self, max_leaf_tris=4, cost_node=1.0, cost_tri=2.0, rotations=1, treelets=1, morton_bits=0):
+        opts = PrtBvhOptions(int(max_leaf_tris), float(cost_node), float(cost_tri), int(rotations), int(treelets),
+                             int(morton_bits))
         st = PrtBvhStats()
         self._check(self.lib.prt_bvh_build(self.h, C.byref(opts), C.byref(st)))
         return {k: getattr(st, k) for k, _ in PrtBvhStats._fields_}
@@ -281,6 +283,9 @@ class Context:
     def render_host(self, params, accum):
         assert accum.dtype == np.float32 and accum.flags.c_contiguous
         self._check(self.lib.prt_render_host(self.h, C.byref(params), _np_ptr(accum)))
+
+    def release_scratch(self):
+        self._check(self.lib.prt_release_scratch(self.h))
 
     def set_wave_paths(self, paths):
         self._check(self.lib.prt_set_wave_paths(self.h, int(paths)))

@@ -2,13 +2,17 @@
 //
 // Pipeline (all on the device; the host only reads a queue length per tree level):
 //   1. bounds_kernel     scene AABB (warp reduce + ordered-int atomics)
-//   2. morton_kernel     30-bit Morton code of each triangle's box centre
-//   3. radix sort        (key, triangle) pairs, 4 x 8-bit stable LSD passes (radix_sort.cuh)
+//   2. morton_kernel     30-bit Morton code of each triangle's box centre; 63-bit (21 bits per
+//                        axis) when the 30-bit grid leaves more than 1/16 of the sorted
+//                        neighbours in the same cell (clustered scenes), or on request
+//   3. radix sort        (key, triangle) pairs, 4 x 8-bit stable LSD passes (radix_sort.cuh);
+//                        63-bit keys: low word first, then the high word (stable)
 //   4. hierarchy_kernel  Karras 2012 "Maximizing parallelism in the construction
 //                        of BVHs, octrees and k-d trees": one thread per internal node
 //   5. refit_kernel      bottom-up with arrival flags: boxes, SAH cost, SAH tree
 //                        rotations (3-leaf treelets) and SAH leaf collapse (<= 7 tris)
-//   6. emit4_kernel      breadth-first collapse of the binary tree into 4-wide records
+//   6. emit_levels_kernel breadth-first collapse of the binary tree into 4-wide records, ONE
+//                        cooperative launch (grid-wide barrier between levels)
 //                        (expand the child of largest surface area), conservative 8-bit
 //                        quantisation of the child boxes in the record's frame, leaf
 //                        triangles copied to contiguous ranges
@@ -17,6 +21,10 @@
 // (recursive binned SAH on the CPU), Aggregator.update accelerators/aggregator.py:25-55
 // (flat soup for zero-thickness primitives: no special path here, flat boxes
 // quantise fine) and BVH.build accelerators/bvh_taichi.py:126-161.
+#include <cooperative_groups.h>
+
+#include <chrono>
+
 #include "context.cuh"
 #include "bvh.cuh"
 #include "radix_sort.cuh"
@@ -25,9 +33,12 @@ namespace prt {
 
 namespace {
 
+// Scratch of one build, carved out of the context's grow-only arena (prt_ctx::build_arena): no
+// cudaMalloc / cudaFree per build -- two dozen of them cost 30 ms of wall time around a 2 ms build.
 struct BuildBuffers {
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t* keys_hi = nullptr;  // 63-bit Morton: high words in sorted order
     void* sort_tmp = nullptr;
     int* left = nullptr;     // [N-1]
     int* right = nullptr;    // [N-1]
@@ -39,21 +50,12 @@ struct BuildBuffers {
     uint8_t* collapsed = nullptr;  // [2N-1]
     unsigned int* flags = nullptr;  // [N-1]
     int* scene_box = nullptr;       // 6 ordered ints
-    unsigned int* max_depth = nullptr;
+    unsigned int* sort_check = nullptr;  // [2] inversions, equal neighbours
     int* queue = nullptr;           // emit: binary node of each wide record
-    unsigned int* tails = nullptr;  // emit: queue tail, triangle tail
+    unsigned int* tails = nullptr;  // emit: queue tail, triangle tail, level begin, level end, depth
     int2* range = nullptr;          // [N-1] sorted positions covered by each internal node (treelets)
     int* roots = nullptr;           // [N-1] treelet roots
     unsigned int* n_roots = nullptr;
-    cudaEvent_t ev[7] = {};         // phase timing; destroyed with the buffers (also on the error paths)
-    void free_all() {
-        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
-        cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
-        cudaFree(sort_tmp); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(bmin);
-        cudaFree(bmax); cudaFree(tcount); cudaFree(icount); cudaFree(collapsed); cudaFree(flags);
-        cudaFree(scene_box); cudaFree(max_depth); cudaFree(queue); cudaFree(tails);
-        cudaFree(range); cudaFree(roots); cudaFree(n_roots);
-    }
 };
 
 __device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int
@@ -119,37 +121,97 @@ __global__ void morton_kernel(const float4* __restrict__ v, uint32_t nt, const i
     vals[t] = t;
 }
 
-__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+__device__ __forceinline__ unsigned long long expand21(unsigned long long x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+// 63-bit code, 21 bits per axis: low word -> keys (sorted first), high word -> hi_by_tri
+__global__ void morton63_kernel(const float4* __restrict__ v, uint32_t nt, const int* __restrict__ box,
+                                uint32_t* keys, uint32_t* vals, uint32_t* lo_by_tri, uint32_t* hi_by_tri) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    float3 smin = make_float3(ord2f(box[0]), ord2f(box[1]), ord2f(box[2]));
+    float3 smax = make_float3(ord2f(box[3]), ord2f(box[4]), ord2f(box[5]));
+    float3 lo, hi;
+    tri_box(v, t, lo, hi);
+    // f64: 21 bits per axis are more than an f32 quotient resolves near the far end of the scene box
+    const double ex = (double)smax.x - smin.x, ey = (double)smax.y - smin.y, ez = (double)smax.z - smin.z;
+    const double cx = ex > 0. ? (0.5 * ((double)lo.x + hi.x) - smin.x) / ex : 0.;
+    const double cy = ey > 0. ? (0.5 * ((double)lo.y + hi.y) - smin.y) / ey : 0.;
+    const double cz = ez > 0. ? (0.5 * ((double)lo.z + hi.z) - smin.z) / ez : 0.;
+    const unsigned long long x = (unsigned long long)fmin(fmax(cx * 2097152., 0.), 2097151.);
+    const unsigned long long y = (unsigned long long)fmin(fmax(cy * 2097152., 0.), 2097151.);
+    const unsigned long long z = (unsigned long long)fmin(fmax(cz * 2097152., 0.), 2097151.);
+    const unsigned long long k = (expand21(x) << 2) | (expand21(y) << 1) | expand21(z);
+    keys[t] = (uint32_t)k;
+    lo_by_tri[t] = (uint32_t)k;
+    hi_by_tri[t] = (uint32_t)(k >> 32);
+    vals[t] = t;
+}
+
+__global__ void gather_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+// keys_hi == nullptr: 30-bit keys.  Equal keys are told apart by their sorted position.
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ keys_hi, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
+    if (keys_hi) {
+        const uint32_t ha = keys_hi[i], hb = keys_hi[j];
+        if (ha != hb) return __clz(ha ^ hb);
+        const uint32_t a = keys[i], b = keys[j];
+        if (a != b) return 32 + __clz(a ^ b);
+        return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    }
     uint32_t a = keys[i], b = keys[j];
     if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
     return __clz(a ^ b);
 }
 
-// sortedness self-check of the radix sort (counts inversions; reported in prt_bvh_stats)
-__global__ void check_sorted_kernel(const uint32_t* __restrict__ keys, uint32_t n, unsigned int* bad) {
+// self-check of the radix sort: out[0] = inversions (reported in prt_bvh_stats), out[1] = equal
+// neighbours (how many triangles the key grid could not separate: decides 30 vs 63 bits)
+__global__ void check_sorted_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ keys_hi, uint32_t n,
+                                    unsigned int* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 < n && keys[i] > keys[i + 1]) atomicAdd(bad, 1u);
+    bool inv = false, eq = false;
+    if (i + 1 < n) {
+        const unsigned long long a = ((unsigned long long)(keys_hi ? keys_hi[i] : 0u) << 32) | keys[i];
+        const unsigned long long b = ((unsigned long long)(keys_hi ? keys_hi[i + 1] : 0u) << 32) | keys[i + 1];
+        inv = a > b; eq = a == b;
+    }
+    const unsigned mi = __ballot_sync(0xffffffffu, inv), me = __ballot_sync(0xffffffffu, eq);
+    if ((threadIdx.x & 31) == 0) {
+        if (mi) atomicAdd(out, (unsigned)__popc(mi));
+        if (me) atomicAdd(out + 1, (unsigned)__popc(me));
+    }
 }
 
 // node ids: internal i -> i (0..n-2), leaf j -> (n-1)+j
-__global__ void hierarchy_kernel(const uint32_t* __restrict__ keys, int n, int* left, int* right,
-                                 int* parent, int2* range) {
+__global__ void hierarchy_kernel(const uint32_t* __restrict__ keys_lo, const uint32_t* __restrict__ keys_hi, int n,
+                                 int* left, int* right, int* parent, int2* range) {
+    struct { const uint32_t* lo; const uint32_t* hi; } keys = {keys_lo, keys_hi};
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    int dmin = delta(keys, n, i, i - d);
+    int d = (delta(keys.lo, keys.hi, n, i, i + 1) - delta(keys.lo, keys.hi, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys.lo, keys.hi, n, i, i - d);
     int lmax = 2;
-    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    while (delta(keys.lo, keys.hi, n, i, i + lmax * d) > dmin) lmax <<= 1;
     int l = 0;
     for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+        if (delta(keys.lo, keys.hi, n, i, i + (l + t) * d) > dmin) l += t;
     int j = i + l * d;
-    int dnode = delta(keys, n, i, j);
+    int dnode = delta(keys.lo, keys.hi, n, i, j);
     int s = 0, t = l;
     do {
         t = (t + 1) >> 1;
-        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (delta(keys.lo, keys.hi, n, i, i + (s + t) * d) > dnode) s += t;
     } while (t > 1);
     int gamma = i + s * d + min(d, 0);
     int lc = (min(i, j) == gamma) ? (n - 1) + gamma : gamma;
@@ -616,16 +678,7 @@ __device__ __forceinline__ void write_record(Node64* out, const float o[3], cons
     p[3] = make_uint4(ref[0], ref[1], ref[2], ref[3]);
 }
 
-// level[0] = begin, level[1] = end of the current level in the queue, level[2] = depth so far
-__global__ void emit_advance_kernel(unsigned int* level, const unsigned int* queue_tail) {
-    level[0] = level[1];
-    level[1] = *queue_tail;
-    if (level[0] < level[1]) ++level[2];
-}
-
-__global__ void emit4_kernel(EmitArgs A, const unsigned int* __restrict__ level) {
-    const unsigned int idx = level[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= level[1]) return;
+__device__ __forceinline__ void emit_record(const EmitArgs& A, unsigned int idx) {
     const int n = A.n;
     const int v = A.queue[idx];
     int ch[4];
@@ -682,6 +735,30 @@ __global__ void emit4_kernel(EmitArgs A, const unsigned int* __restrict__ level)
     write_record(A.nodes + idx, o, ext, clo, chi, ref, nc);
 }
 
+// All levels in ONE cooperative launch (the grid is sized to be resident): a grid-wide barrier
+// separates the levels, thread 0 publishes the next level's range in between.  Replaces one
+// emit + one advance launch per level (38 launches, 0.2 ms of gaps at 1M triangles).
+// level[0] = begin, level[1] = end of the current level in the queue, level[2] = depth so far.
+__global__ void __launch_bounds__(128)
+emit_levels_kernel(EmitArgs A, unsigned int* level, int max_levels) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    for (int lv = 0; lv < max_levels; ++lv) {
+        const unsigned int begin = __ldcg(level), end = __ldcg(level + 1);
+        if (begin >= end) break;  // (grid-uniform)
+        for (unsigned int idx = begin + tid; idx < end; idx += nthreads) emit_record(A, idx);
+        grid.sync();
+        if (tid == 0) {
+            const unsigned int tail = __ldcg(A.queue_tail);
+            __stcg(level, end);
+            __stcg(level + 1, tail);
+            if (end < tail) __stcg(level + 2, __ldcg(level + 2) + 1u);
+        }
+        grid.sync();
+    }
+}
+
 // n == 1: one record whose only child is the only triangle
 __global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nodes, uint4* tri_a, float2* tri_b) {
     float3 lo, hi;
@@ -707,74 +784,109 @@ __global__ void emit_single_kernel(const float4* __restrict__ verts, Node64* nod
         cudaError_t _e = (expr);                                                             \
         if (_e != cudaSuccess) {                                                             \
             ctx->set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
-            B.free_all();                                                                    \
             return PRT_ERR_CUDA;                                                             \
         }                                                                                    \
     } while (0)
 
+// grow-only device buffer of the context (never shrinks; prt_release_scratch / prt_destroy free it)
+template <class T>
+static cudaError_t reserve(T*& ptr, size_t& cap_bytes, size_t bytes) {
+    if (cap_bytes >= bytes && ptr) return cudaSuccess;
+    cudaFree(ptr);
+    ptr = nullptr; cap_bytes = 0;
+    const cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e == cudaSuccess) cap_bytes = bytes;
+    return e;
+}
+
 static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* stats, bool* too_deep) {
+    const auto wall0 = std::chrono::steady_clock::now();
     BuildBuffers B;
     const uint32_t nt = ctx->nt;
     const int n = (int)nt;
     *too_deep = false;
-    cudaFree(ctx->nodes); ctx->nodes = nullptr;
-    cudaFree(ctx->tri_a); ctx->tri_a = nullptr;
-    cudaFree(ctx->tri_b); ctx->tri_b = nullptr;
     ctx->n_nodes = 0;
     ctx->bvh_built = false;
     prt_bvh_stats st = {};
     st.n_tris = nt;
     st.max_leaf_tris = opt.max_leaf_tris;
+    st.morton_bits = 30;
     if (nt == 0) {
         ctx->bvh_built = true;
         ctx->bvh_stats = st;
         if (stats) *stats = st;
         return PRT_OK;
     }
-    cudaEvent_t* ev = B.ev;
-    for (auto& e : B.ev) BUILD_TRY(cudaEventCreate(&e));
-    const size_t nn = 2 * (size_t)nt - 1;
-    BUILD_TRY(cudaMalloc(&ctx->tri_a, sizeof(uint4) * 2 * (size_t)nt));
-    BUILD_TRY(cudaMalloc(&ctx->tri_b, sizeof(float2) * (size_t)nt));
-    BUILD_TRY(cudaMalloc(&B.scene_box, 6 * sizeof(int)));
-    BUILD_TRY(cudaMalloc(&B.max_depth, sizeof(unsigned int)));
-    BUILD_TRY(cudaMemset(B.max_depth, 0, sizeof(unsigned int)));
-    for (int k = 0; k < 2; ++k) {
-        BUILD_TRY(cudaMalloc(&B.keys[k], sizeof(uint32_t) * nt));
-        BUILD_TRY(cudaMalloc(&B.vals[k], sizeof(uint32_t) * nt));
-    }
-    BUILD_TRY(cudaMalloc(&B.sort_tmp, radix_sort_temp_bytes(nt)));
-    // emit-stage buffers are allocated here too: cudaMalloc inside the timed phases costs milliseconds
-    BUILD_TRY(cudaMalloc(&B.queue, sizeof(int) * (size_t)nt));
-    BUILD_TRY(cudaMalloc(&B.tails, 5 * sizeof(unsigned int)));
-    BUILD_TRY(cudaMalloc(&ctx->nodes, sizeof(Node64) * (size_t)nt));  // upper bound; trimmed below
-    BUILD_TRY(cudaMalloc(&B.left, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
-    BUILD_TRY(cudaMalloc(&B.right, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
-    BUILD_TRY(cudaMalloc(&B.parent, sizeof(int) * nn));
-    BUILD_TRY(cudaMalloc(&B.bmin, sizeof(float4) * nn));
-    BUILD_TRY(cudaMalloc(&B.bmax, sizeof(float4) * nn));
-    BUILD_TRY(cudaMalloc(&B.tcount, sizeof(uint32_t) * nn));
-    BUILD_TRY(cudaMalloc(&B.icount, sizeof(uint32_t) * nn));
-    BUILD_TRY(cudaMalloc(&B.collapsed, nn));
-    BUILD_TRY(cudaMalloc(&B.range, sizeof(int2) * (nt > 1 ? nt - 1 : 1)));
-    BUILD_TRY(cudaMalloc(&B.roots, sizeof(int) * (nt > 1 ? nt - 1 : 1)));
-    BUILD_TRY(cudaMalloc(&B.n_roots, sizeof(unsigned int)));
-    BUILD_TRY(cudaMemset(B.n_roots, 0, sizeof(unsigned int)));
-    BUILD_TRY(cudaMalloc(&B.flags, sizeof(unsigned int) * (nt > 1 ? nt - 1 : 1)));
-    BUILD_TRY(cudaMemset(B.flags, 0, sizeof(unsigned int) * (nt > 1 ? nt - 1 : 1)));
-    BUILD_TRY(cudaMemset(B.collapsed, 0, nn));
+    cudaEvent_t* ev = ctx->build_ev;
+    for (int k = 0; k < 7; ++k)
+        if (!ev[k]) BUILD_TRY(cudaEventCreate(&ev[k]));
+    const size_t nn = 2 * (size_t)nt - 1, ni = nt > 1 ? nt - 1 : 1;
+    BUILD_TRY(reserve(ctx->tri_a, ctx->tri_a_bytes, sizeof(uint4) * 2 * (size_t)nt));
+    BUILD_TRY(reserve(ctx->tri_b, ctx->tri_b_bytes, sizeof(float2) * (size_t)nt));
+    // ---- carve the scratch out of the arena; everything that must start at zero comes first
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_flags = take(sizeof(unsigned int) * ni), o_coll = take(nn), o_small = take(256);
+    const size_t zero_bytes = off;
+    const size_t o_keys0 = take(4ull * nt), o_keys1 = take(4ull * nt), o_vals0 = take(4ull * nt), o_vals1 = take(4ull * nt);
+    const size_t o_lo = take(4ull * nt), o_hi = take(4ull * nt), o_khi = take(4ull * nt);
+    const size_t o_sort = take(radix_sort_temp_bytes(nt)), o_queue = take(4ull * nt);
+    const size_t o_left = take(4ull * ni), o_right = take(4ull * ni), o_parent = take(4ull * nn);
+    const size_t o_bmin = take(16ull * nn), o_bmax = take(16ull * nn), o_tc = take(4ull * nn), o_ic = take(4ull * nn);
+    const size_t o_range = take(8ull * ni), o_roots = take(4ull * ni);
+    BUILD_TRY(reserve(ctx->build_arena, ctx->build_arena_bytes, off));
+    char* base = (char*)ctx->build_arena;
+    B.flags = (unsigned int*)(base + o_flags); B.collapsed = (uint8_t*)(base + o_coll);
+    unsigned int* small = (unsigned int*)(base + o_small);  // zeroed: [0..1] sort check, [2] n_roots, [8..12] emit tails, [16..21] scene box
+    B.sort_check = small; B.n_roots = small + 2; B.tails = small + 8; B.scene_box = (int*)(small + 16);
+    B.keys[0] = (uint32_t*)(base + o_keys0); B.keys[1] = (uint32_t*)(base + o_keys1);
+    B.vals[0] = (uint32_t*)(base + o_vals0); B.vals[1] = (uint32_t*)(base + o_vals1);
+    uint32_t* lo_by_tri = (uint32_t*)(base + o_lo); uint32_t* hi_by_tri = (uint32_t*)(base + o_hi);
+    B.keys_hi = (uint32_t*)(base + o_khi);
+    B.sort_tmp = base + o_sort; B.queue = (int*)(base + o_queue);
+    B.left = (int*)(base + o_left); B.right = (int*)(base + o_right); B.parent = (int*)(base + o_parent);
+    B.bmin = (float4*)(base + o_bmin); B.bmax = (float4*)(base + o_bmax);
+    B.tcount = (uint32_t*)(base + o_tc); B.icount = (uint32_t*)(base + o_ic);
+    B.range = (int2*)(base + o_range); B.roots = (int*)(base + o_roots);
+    BUILD_TRY(cudaMemsetAsync(base, 0, zero_bytes));
 
     const int T = 256;
     const unsigned gN = (nt + T - 1) / T;
     cudaEventRecord(ev[0]);
     init_box_kernel<<<1, 32>>>(B.scene_box);
     bounds_kernel<<<min(gN, (unsigned)ctx->num_sms * 8u), T>>>(ctx->verts_gid, nt, B.scene_box);
-    morton_kernel<<<gN, T>>>(ctx->verts_gid, nt, B.scene_box, B.keys[0], B.vals[0]);
-    cudaEventRecord(ev[1]);
-    const int sorted = radix_sort_pairs(B.keys, B.vals, nt, 30, B.sort_tmp, 0);  // result in keys/vals[sorted]
-    check_sorted_kernel<<<gN, T>>>(B.keys[sorted], nt, B.max_depth);  // max_depth doubles as the inversion counter
+    int sorted = 0;
+    const uint32_t* keys_hi = nullptr;
+    bool use63 = opt.morton_bits == 63;
+    if (!use63) {
+        morton_kernel<<<gN, T>>>(ctx->verts_gid, nt, B.scene_box, B.keys[0], B.vals[0]);
+        cudaEventRecord(ev[1]);
+        sorted = radix_sort_pairs(B.keys, B.vals, nt, 30, B.sort_tmp, 0);  // result in keys/vals[sorted]
+        check_sorted_kernel<<<gN, T>>>(B.keys[sorted], nullptr, nt, B.sort_check);
+        if (opt.morton_bits == 0 && nt >= 4096) {  // auto: did the 30-bit grid separate the triangles?
+            unsigned int chk[2] = {0, 0};
+            BUILD_TRY(cudaMemcpy(chk, B.sort_check, sizeof chk, cudaMemcpyDeviceToHost));
+            use63 = chk[1] > nt / 16;
+        }
+    }
+    if (use63) {
+        BUILD_TRY(cudaMemsetAsync(B.sort_check, 0, 2 * sizeof(unsigned int)));
+        morton63_kernel<<<gN, T>>>(ctx->verts_gid, nt, B.scene_box, B.keys[0], B.vals[0], lo_by_tri, hi_by_tri);
+        if (opt.morton_bits == 63) cudaEventRecord(ev[1]);
+        int cur = radix_sort_pairs(B.keys, B.vals, nt, 32, B.sort_tmp, 0);  // by the low word ...
+        gather_kernel<<<gN, T>>>(hi_by_tri, B.vals[cur], nt, B.keys[cur]);
+        uint32_t* k2[2] = {B.keys[cur], B.keys[cur ^ 1]};
+        uint32_t* v2[2] = {B.vals[cur], B.vals[cur ^ 1]};
+        const int c2 = radix_sort_pairs(k2, v2, nt, 32, B.sort_tmp, 0);     // ... then, stably, by the high word
+        sorted = cur ^ c2;
+        cudaMemcpyAsync(B.keys_hi, B.keys[sorted], 4ull * nt, cudaMemcpyDeviceToDevice);
+        gather_kernel<<<gN, T>>>(lo_by_tri, B.vals[sorted], nt, B.keys[sorted]);
+        keys_hi = B.keys_hi;
+        check_sorted_kernel<<<gN, T>>>(B.keys[sorted], keys_hi, nt, B.sort_check);
+        st.morton_bits = 63;
+    }
     cudaEventRecord(ev[2]);
-    if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[sorted], n, B.left, B.right, B.parent, B.range);
+    if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[sorted], keys_hi, n, B.left, B.right, B.parent, B.range);
     if (n > 2 && opt.treelets) {
         treelet_roots_kernel<<<gN, T>>>(B.range, B.parent, n, B.roots, B.n_roots);
         treelet_sah_kernel<<<ctx->num_sms * 8, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
@@ -787,58 +899,57 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     // rotations = k > 1 repeats the bottom-up pass: every pass re-derives boxes and costs from the
     // leaves and applies the best rotation per node again (the topology from the last pass is kept)
     for (int pass = 0; pass < (P.rotations > 1 ? P.rotations : 1); ++pass) {
-        if (pass) cudaMemsetAsync(B.flags, 0, sizeof(unsigned int) * (nt > 1 ? nt - 1 : 1));
+        if (pass) cudaMemsetAsync(B.flags, 0, sizeof(unsigned int) * ni);
         refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[sorted], B.left, B.right, B.parent, B.bmin, B.bmax,
                                 B.tcount, B.icount, B.collapsed, B.flags, P);
     }
     cudaEventRecord(ev[4]);
     BUILD_TRY(cudaGetLastError());
+    // the one mid-build read-back: number of surviving records (sizes the node array) + root box / cost
     uint32_t n_rec = 1;
     float4 root_lo = {}, root_hi = {};
     if (n > 1) {
-        BUILD_TRY(cudaMemcpy(&n_rec, B.icount, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        BUILD_TRY(cudaMemcpy(&root_lo, B.bmin, sizeof(float4), cudaMemcpyDeviceToHost));
+        BUILD_TRY(cudaMemcpyAsync(&n_rec, B.icount, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        BUILD_TRY(cudaMemcpyAsync(&root_lo, B.bmin, sizeof(float4), cudaMemcpyDeviceToHost));
         BUILD_TRY(cudaMemcpy(&root_hi, B.bmax, sizeof(float4), cudaMemcpyDeviceToHost));
     }
+    BUILD_TRY(reserve(ctx->nodes, ctx->nodes_bytes, sizeof(Node64) * (size_t)(n_rec ? n_rec : 1)));
     unsigned int depth = 0, n_wide = 1;
     cudaEventRecord(ev[5]);
+    unsigned int fin[5] = {1u, 0u, 0u, 0u, 1u};
     if (n > 1) {
         const unsigned int init[5] = {1u, 0u, /*level:*/ 0u, 1u, 1u};  // queue tail, tri tail, begin, end, depth
         BUILD_TRY(cudaMemsetAsync(B.queue, 0, sizeof(int)));  // record 0 = binary root (node 0)
-        BUILD_TRY(cudaMemcpy(B.tails, init, sizeof init, cudaMemcpyHostToDevice));
+        BUILD_TRY(cudaMemcpyAsync(B.tails, init, sizeof init, cudaMemcpyHostToDevice));
         EmitArgs A;
         A.verts = ctx->verts_gid; A.vals = B.vals[sorted]; A.left = B.left; A.right = B.right;
         A.bmin = B.bmin; A.bmax = B.bmax; A.tcount = B.tcount; A.collapsed = B.collapsed; A.n = n;
         A.queue = B.queue; A.queue_tail = B.tails; A.tri_tail = B.tails + 1; A.nodes = ctx->nodes;
         A.tri_a = ctx->tri_a; A.tri_b = ctx->tri_b;
-        // One launch per level, driven from the device (no host round trip per level): a level has
-        // at most n_rec records and the tree at most kMaxStack/3 levels that traversal can use.
-        // Levels shrink/grow by <= 4x, so the grid is sized from the previous bound.
-        const int max_levels = kMaxStack / 3 + 1;
-        size_t bound = 1;
-        for (int lv = 0; lv < max_levels; ++lv) {
-            const unsigned g = (unsigned)((bound + T - 1) / T);
-            emit4_kernel<<<g, T>>>(A, B.tails + 2);
-            emit_advance_kernel<<<1, 1>>>(B.tails + 2, B.tails);
-            bound = bound * 4 < (size_t)n_rec ? bound * 4 : (size_t)n_rec;
+        // the tree has at most kMaxStack/3 levels that traversal can use
+        int max_levels = kMaxStack / 3 + 1;
+        if (ctx->grid_emit == 0) {
+            int b = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, emit_levels_kernel, 128, 0);
+            ctx->grid_emit = ctx->num_sms * (b > 0 ? b : 1);
         }
-        unsigned int fin[5];
-        BUILD_TRY(cudaMemcpy(fin, B.tails, sizeof fin, cudaMemcpyDeviceToHost));
+        unsigned int* level = B.tails + 2;
+        void* args[] = {&A, &level, &max_levels};
+        BUILD_TRY(cudaLaunchCooperativeKernel((void*)emit_levels_kernel, dim3(ctx->grid_emit), dim3(128), args, 0, 0));
+        BUILD_TRY(cudaMemcpyAsync(fin, B.tails, sizeof fin, cudaMemcpyDeviceToHost));
+    } else {
+        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tri_a, ctx->tri_b);
+    }
+    cudaEventRecord(ev[6]);
+    unsigned int chk[2] = {0, 0};
+    BUILD_TRY(cudaMemcpyAsync(chk, B.sort_check, sizeof chk, cudaMemcpyDeviceToHost));
+    BUILD_TRY(cudaDeviceSynchronize());
+    if (n > 1) {
         n_wide = fin[0];
         depth = fin[4];
         if (fin[2] < fin[3]) depth = kMaxStack;  // levels left over: deeper than traversal supports
     } else {
-        emit_single_kernel<<<1, 1>>>(ctx->verts_gid, ctx->nodes, ctx->tri_a, ctx->tri_b);
         depth = 1;
-    }
-    cudaEventRecord(ev[6]);
-    BUILD_TRY(cudaDeviceSynchronize());
-    if ((size_t)(nt - n_wide) * sizeof(Node64) > (64u << 20)) {  // give back a large unused tail
-        Node64* fit = nullptr;
-        BUILD_TRY(cudaMalloc(&fit, sizeof(Node64) * (size_t)n_wide));
-        BUILD_TRY(cudaMemcpy(fit, ctx->nodes, sizeof(Node64) * (size_t)n_wide, cudaMemcpyDeviceToDevice));
-        cudaFree(ctx->nodes);
-        ctx->nodes = fit;
     }
     n_rec = n_wide;
     float ms[6];
@@ -849,12 +960,8 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     st.ms_emit = ms[5];
     st.ms_total = ms[0] + ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
     st.depth = depth;
-    {
-        unsigned int inversions = 0;
-        cudaMemcpy(&inversions, B.max_depth, sizeof inversions, cudaMemcpyDeviceToHost);
-        st.morton_sorted = inversions == 0 ? 1u : 0u;
-    }
-    B.free_all();
+    st.morton_sorted = chk[0] == 0 ? 1u : 0u;
+    st.ms_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     if (3 * depth + 1 > (unsigned)kMaxStack) { *too_deep = true; return PRT_OK; }  // <= 3 pushes per level
     ctx->n_nodes = n_rec;
     ctx->bvh_built = true;
@@ -867,8 +974,9 @@ int build_bvh(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats) {
     prt_bvh_options o;
     // cost_tri 2: coplanar pairs (quads) still collapse into one leaf, random soups do not
     // (profiles/r1_sweeps.txt: soup-1M prefers 1-triangle leaves, Cornell 2..4)
-    o.max_leaf_tris = 4; o.cost_node = 1.0f; o.cost_tri = 2.0f; o.rotations = 1; o.treelets = 1;
+    o.max_leaf_tris = 4; o.cost_node = 1.0f; o.cost_tri = 2.0f; o.rotations = 1; o.treelets = 1; o.morton_bits = 0;
     if (opts) o = *opts;
+    if (o.morton_bits != 0 && o.morton_bits != 30 && o.morton_bits != 63) { ctx->set_error("bvh: morton_bits must be 0 (auto), 30 or 63"); return PRT_ERR_INVALID; }
     if (o.max_leaf_tris < 1 || o.max_leaf_tris > 7) { ctx->set_error("bvh: max_leaf_tris must be in 1..7"); return PRT_ERR_INVALID; }
     if (!ctx->scene_set) { ctx->set_error("bvh: no scene"); return PRT_ERR_STATE; }
     bool too_deep = false;

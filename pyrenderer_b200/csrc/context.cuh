@@ -20,6 +20,15 @@ struct prt_ctx {
     uint32_t* light_tris = nullptr;
     bool scene_set = false;
 
+    // capacities (bytes) of the grow-only device buffers: a new scene or a rebuild of the same size
+    // reuses them (no cudaMalloc / cudaFree on the set-scene / build path after the first call)
+    size_t verts_bytes = 0, shade_bytes = 0, mats_bytes = 0, lights_bytes = 0;
+    size_t tri_a_bytes = 0, tri_b_bytes = 0, nodes_bytes = 0;
+    void* build_arena = nullptr;   // scratch of bvh_build.cu
+    size_t build_arena_bytes = 0;
+    cudaEvent_t build_ev[7] = {};  // phase timing of the build
+    int grid_emit = 0;             // resident CTAs of the cooperative emit kernel
+
     // BVH (device)
     uint4* tri_a = nullptr;        // [nt*2] leaf order: p0.xyz, p1.xyz, p2.xy
     float2* tri_b = nullptr;       // [nt]   leaf order: p2.z, bits(global id)

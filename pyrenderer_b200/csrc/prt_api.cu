@@ -57,29 +57,47 @@ __global__ void pack_shade_kernel(const float* __restrict__ v, const float* __re
     shade[t] = make_float4(n.x, n.y, n.z, __uint_as_float(tri_mat ? tri_mat[t] : 0u));
 }
 
-static void free_scene(prt_ctx* c) {
-    cudaFree(c->verts_gid); cudaFree(c->shade); cudaFree(c->mats); cudaFree(c->light_tris);
-    cudaFree(c->tri_a); cudaFree(c->tri_b); cudaFree(c->nodes);
-    c->verts_gid = nullptr; c->shade = nullptr; c->mats = nullptr; c->light_tris = nullptr;
-    c->tri_a = nullptr; c->tri_b = nullptr; c->nodes = nullptr;
+// forget the scene; the device buffers stay (grow-only) for the next one
+static void reset_scene(prt_ctx* c) {
     c->nt = c->nm = c->nl = c->n_nodes = 0;
     c->scene_set = false; c->bvh_built = false;
+}
+
+static void free_scene(prt_ctx* c) {
+    reset_scene(c);
+    cudaFree(c->verts_gid); cudaFree(c->shade); cudaFree(c->mats); cudaFree(c->light_tris);
+    cudaFree(c->tri_a); cudaFree(c->tri_b); cudaFree(c->nodes); cudaFree(c->build_arena);
+    c->verts_gid = nullptr; c->shade = nullptr; c->mats = nullptr; c->light_tris = nullptr;
+    c->tri_a = nullptr; c->tri_b = nullptr; c->nodes = nullptr; c->build_arena = nullptr;
+    c->verts_bytes = c->shade_bytes = c->mats_bytes = c->lights_bytes = 0;
+    c->tri_a_bytes = c->tri_b_bytes = c->nodes_bytes = c->build_arena_bytes = 0;
+}
+
+template <class T>
+static cudaError_t reserve(T*& ptr, size_t& cap_bytes, size_t bytes) {
+    if (cap_bytes >= bytes && ptr) return cudaSuccess;
+    cudaFree(ptr);
+    ptr = nullptr; cap_bytes = 0;
+    const cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e == cudaSuccess) cap_bytes = bytes;
+    return e;
 }
 
 static int set_scene_common(prt_ctx* ctx, const float* verts_dev, const float* normals_dev,
                             const uint32_t* tri_mat_dev, uint32_t nt, const prt_material* mats_host,
                             uint32_t nm, const uint32_t* light_host, uint32_t nl, cudaStream_t s) {
-    free_scene(ctx);
+    reset_scene(ctx);
     prt_material def;
     memset(&def, 0, sizeof def);
     def.albedo[0] = def.albedo[1] = def.albedo[2] = 0.5f;
     def.type = PRT_MAT_LAMBERT; def.ior = 1.0f; def.two_sided = 1;
     if (!mats_host || nm == 0) { mats_host = &def; nm = 1; }
     size_t ntz = nt ? nt : 1;
-    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->verts_gid, sizeof(float4) * 3 * ntz));
-    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->shade, sizeof(float4) * ntz));
-    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->mats, sizeof(prt_material) * nm));
-    PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->light_tris, sizeof(uint32_t) * (nl ? nl : 1)));
+    PRT_CUDA_TRY(ctx, cudaStreamSynchronize(s));  // (a buffer that has to grow is freed: nothing may still read it)
+    PRT_CUDA_TRY(ctx, reserve(ctx->verts_gid, ctx->verts_bytes, sizeof(float4) * 3 * ntz));
+    PRT_CUDA_TRY(ctx, reserve(ctx->shade, ctx->shade_bytes, sizeof(float4) * ntz));
+    PRT_CUDA_TRY(ctx, reserve(ctx->mats, ctx->mats_bytes, sizeof(prt_material) * nm));
+    PRT_CUDA_TRY(ctx, reserve(ctx->light_tris, ctx->lights_bytes, sizeof(uint32_t) * (nl ? nl : 1)));
     PRT_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->mats, mats_host, sizeof(prt_material) * nm, cudaMemcpyHostToDevice, s));
     if (nl) PRT_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->light_tris, light_host, sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, s));
     if (nt) {
@@ -192,6 +210,7 @@ void prt_destroy(prt_ctx* ctx) {
     free_scene(ctx);
     cudaFree(ctx->shard_accum);
     for (auto& e : ctx->prof_events) cudaEventDestroy(e);
+    for (auto& e : ctx->build_ev) if (e) cudaEventDestroy(e);
     for (auto& l : ctx->flag_list) cudaFree(l);
     cudaFree(ctx->counters); cudaFree(ctx->flag_count);
     cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]); cudaFree(ctx->fetch_counters);
@@ -417,6 +436,20 @@ int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity,
     ctx->log_segments = (float4*)segments_dev;
     ctx->log_count = segments_dev ? count_dev : nullptr;
     ctx->log_capacity = segments_dev ? (uint32_t)capacity : 0u;
+    return PRT_OK;
+}
+
+int prt_release_scratch(prt_ctx* ctx) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->build_arena);
+    ctx->build_arena = nullptr; ctx->build_arena_bytes = 0;
+    for (int k = 0; k < 2; ++k) { cudaFree(ctx->stage[k]); ctx->stage[k] = nullptr; ctx->stage_bytes[k] = 0; }
+    cudaFree(ctx->shard_accum);
+    ctx->shard_accum = nullptr; ctx->shard_bytes = 0;
+    for (unsigned k = 0; k < prt_ctx::kFlagRing; ++k) { cudaFree(ctx->flag_list[k]); ctx->flag_list[k] = nullptr; ctx->flag_cap[k] = 0; }
+    wavefront_free(ctx);
     return PRT_OK;
 }
 

@@ -442,3 +442,50 @@ def test_fuzz_small_scenes_exact_ids(gpu_ctx):
         ids_f = gpu_closest(gpu_ctx, rays, 0)[0]
         # measured 0 mismatches on all of them; duplicated triangles tie exactly (lowest id wins in both modes)
         assert np.sum(ids_f != ids_o) <= 1, f"fuzz{nt}/{kind}: plain FP32 mismatches {np.sum(ids_f != ids_o)} of 1500"
+
+
+def test_morton_63_bit_keys_and_grow_only_buffers(gpu_ctx):
+    """63-bit Morton keys (21 bits per axis): picked automatically when the 30-bit grid cannot
+    separate the triangles (a dense cluster inside a huge scene box), selectable by hand, and
+    never a change of the hits.  Also: rebuilds reuse the context's buffers (prt_release_scratch
+    gives the scratch back without touching the scene)."""
+    rng = np.random.default_rng(63)
+    n = 60000
+    tris = (rng.uniform(0.4, 0.4002, (n, 1, 3)) + rng.uniform(-2e-6, 2e-6, (n, 3, 3))).astype(np.float32)
+    tris[:8] = random_soup(8, seed=1) * 1000.0  # a few far-away triangles blow the scene box up to 1000 units
+    rays = random_rays(20000, seed=64)
+    d = tris[rng.integers(8, n, rays.shape[0])].mean(axis=1) - rays[:, 0:3]
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)  # aim at the cluster
+    ref = oracle.closest_hit(tris, rays)
+    assert np.mean(ref[0] >= 8) > 0.5
+    gpu_ctx.set_triangles(tris)
+    st = gpu_ctx.build_bvh()
+    assert st["morton_bits"] == 63 and st["morton_sorted"] == 1 and st["ms_wall"] > 0
+    check_against_oracle(gpu_ctx, tris, rays, EXACT, "cluster-auto63", ref)
+    gpu_ctx.reset_counters()
+    gpu_closest(gpu_ctx, rays, COUNT)
+    v63 = gpu_ctx.counters()["node_visits"] / rays.shape[0]
+    st30 = gpu_ctx.build_bvh(morton_bits=30)
+    assert st30["morton_bits"] == 30
+    check_against_oracle(gpu_ctx, tris, rays, EXACT, "cluster-30", ref)
+    gpu_ctx.reset_counters()
+    gpu_closest(gpu_ctx, rays, COUNT)
+    v30 = gpu_ctx.counters()["node_visits"] / rays.shape[0]
+    print(f"[morton] clustered scene: record visits per ray 30-bit {v30:.1f} -> 63-bit {v63:.1f}")
+    assert v63 < v30
+    # an ordinary soup stays on 30 bits in auto mode; forcing 63 changes no hit
+    tris = random_soup(50000, seed=65)
+    rays = random_rays(50000, seed=66)
+    gpu_ctx.set_triangles(tris)
+    assert gpu_ctx.build_bvh()["morton_bits"] == 30
+    ids30, t30, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+    assert gpu_ctx.build_bvh(morton_bits=63)["morton_bits"] == 63
+    ids63, t63, _, _ = gpu_closest(gpu_ctx, rays, EXACT)
+    assert np.array_equal(ids30, ids63) and np.array_equal(t30, t63)
+    with pytest.raises(Exception):
+        gpu_ctx.build_bvh(morton_bits=48)
+    gpu_ctx.release_scratch()
+    ids2, _, _, _ = gpu_closest(gpu_ctx, rays, EXACT)  # scene + BVH survive; scratch is re-grown on demand
+    assert np.array_equal(ids2, ids63)
+    st2 = gpu_ctx.build_bvh()
+    assert st2["n_tris"] == 50000
