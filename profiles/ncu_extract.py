@@ -34,7 +34,7 @@ WANT = {
     "sm__cycles_active.min": "sm_cycles_active_min",
     "sm__cycles_active.max": "sm_cycles_active_max",
     "sm__cycles_elapsed.max": "sm_cycles_elapsed",
-    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1tex_throughput_pct",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
@@ -48,16 +48,18 @@ def main():
     note = sys.argv[4] if len(sys.argv) > 4 else ""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
+    scale = {"ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "s": 1e9, "second": 1e9,
+             "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}  # ncu scales units per value
     launches = []
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         if sub not in name:
             continue
         d = {"kernel": name, "grid": r[hdr.index("Grid Size")], "block": r[hdr.index("Block Size")]}
-        for h, v in zip(hdr, r):
+        for h, u, v in zip(hdr, units, r):
             if h in WANT and v not in ("", "n/a"):
-                d[WANT[h]] = float(v.replace(",", ""))
+                d[WANT[h]] = float(v.replace(",", "")) * scale.get(u, 1.0)
         launches.append(d)
     if not launches:
         raise SystemExit(f"no kernel matching {sub!r} in {rep}")

@@ -22,6 +22,8 @@ def report(label, rays, n):
     hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
     hx = torch.empty((n, 4), dtype=torch.float32, device=dev)
     ms_f = timed(rays, n, hits, 0)
+    ctx.trace_closest(rays, n, hx, _abi.TRACE_EXACT)  # warm: the exact mode's flag list is allocated on first use
+    torch.cuda.synchronize()
     ctx.reset_counters()
     ms_x = timed(rays, n, hx, _abi.TRACE_EXACT)
     flagged = ctx.counters()["flagged_rays"] / 4

@@ -1,5 +1,5 @@
-"""Small driver for ncu: 1M-triangle soup, closest-hit batches of 2^24 incoherent rays (= one bench.py step).
-usage: python profiles/prof_trace.py [n_launches]"""
+"""Small driver for ncu: N-triangle soup, closest-hit batches of 2^24 incoherent rays (= one bench.py step).
+usage: python profiles/prof_trace.py [n_launches] [exact|fp32] [n_tris]"""
 import os
 import sys
 
@@ -11,10 +11,12 @@ from bench import soup  # noqa: E402
 from pyrenderer_b200 import _abi  # noqa: E402
 
 n_launch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+flags = _abi.TRACE_EXACT if (len(sys.argv) > 2 and sys.argv[2] == "exact") else 0
+n_tris = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
 N = 1 << 24  # the bench launch: 2^24 rays
 dev = torch.device("cuda", 0)
 ctx = _abi.Context(0)
-ctx.set_triangles_dev(torch.from_numpy(soup(1_000_000)).to(dev), 1_000_000)
+ctx.set_triangles_dev(torch.from_numpy(soup(n_tris)).to(dev), n_tris)
 print(ctx.build_bvh())
 g = torch.Generator(device=dev)
 g.manual_seed(11)
@@ -28,7 +30,7 @@ hits = torch.empty((N, 4), dtype=torch.float32, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(n_launch):
     e0.record()
-    ctx.trace_closest(r, N, hits, 0)
+    ctx.trace_closest(r, N, hits, flags)
     e1.record()
     torch.cuda.synchronize()
     print(f"launch {i}: {e0.elapsed_time(e1):.3f} ms  {N / e0.elapsed_time(e1) / 1e3:.1f} Mrays/s")

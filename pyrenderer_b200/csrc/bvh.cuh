@@ -34,7 +34,10 @@ __device__ __forceinline__ float clamp_dir(float d) {
 
 struct RayBox {  // per-ray constants of the slab test
     float3 o, idir;
+    // octant, from the sign of idir (clamp_dir keeps the sign, also of -0.0: a flag taken from
+    // `d < 0` would call -0.0 positive while its reciprocal is -1e20, and swap near and far)
     bool negx, negy, negz;
+    __device__ __forceinline__ void set_octant() { negx = idir.x < 0.0f; negy = idir.y < 0.0f; negz = idir.z < 0.0f; }
 };
 
 __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
@@ -42,7 +45,7 @@ __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
     r.o = o;
     r.idir = make_float3(__fdiv_rn(1.0f, clamp_dir(d.x)), __fdiv_rn(1.0f, clamp_dir(d.y)),
                          __fdiv_rn(1.0f, clamp_dir(d.z)));
-    r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
+    r.set_octant();
     return r;
 }
 
@@ -50,7 +53,7 @@ __device__ __forceinline__ RayBox make_raybox_fast(float3 o, float3 d) {  // per
     RayBox r;
     r.o = o;
     r.idir = make_float3(rcp_fast(clamp_dir(d.x)), rcp_fast(clamp_dir(d.y)), rcp_fast(clamp_dir(d.z)));
-    r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
+    r.set_octant();
     return r;
 }
 
@@ -58,7 +61,10 @@ __device__ __forceinline__ float qf(uint32_t w, int byte) {
     return (float)((w >> (8 * byte)) & 0xffu);  // I2F.U8 with a static byte selector
 }
 
-// Node fetch.  The traversal is bound by L1TEX wavefronts (one tag look-up per distinct
+// Node fetch.  (Tried in round 2: serving the first 21 / 85 records -- the top 3 / 4 levels, which
+// every ray walks -- from a per-CTA copy in shared memory: 8.52 -> 8.80 ms on soup-1M; the mixed
+// LDS / LDG paths cost more issue slots than the shorter latency gives back.)
+// The traversal is bound by L1TEX wavefronts (one tag look-up per distinct
 // 128-byte line per load instruction, profiles/r1_trace_persistent_bvh4_ncu.txt: L1/TEX
 // throughput 89 %), so the 64-byte node is read with TWO 256-bit loads (sm_100
 // LDG.E.256, PTX ld.global.v8.b32) instead of four 128-bit ones.
@@ -203,9 +209,13 @@ __device__ __forceinline__ void node_test4(const Node64* __restrict__ node, cons
 // Hot paths never test for overflow: a push that finds fewer than three free levels first
 // SPILLS the bottom kSpill levels to a local-memory array (and shifts the rest down), a pop that
 // finds the shared part empty UNSPILLS kSpill levels -- both rare, out-of-line in effect.  The
-// spilled count lives in ovf[0].x (local memory, not a register).  Keeping the entry distance
-// lets a pop discard, without touching memory, every subtree that a closer hit found in the
-// meantime has made irrelevant.
+// spilled count lives in ovf[0].x (local memory, not a register).  With SENTINEL the bottom entry
+// of the stack is (kDone, -inf), which ends the traversal through the ordinary pop path, so the
+// count is only read after a real spill (reading it at the end of every ray is 1.5 .. 3.4 % of the
+// stall samples, one lane at a time): measured +1.3 % on the EXACT kernel, -1.8 % on the plain one
+// (profiles/r2_sweeps.txt), so only the EXACT kernel uses it.  Keeping the entry distance lets a
+// pop discard, without touching memory, every subtree that a closer hit found in the meantime
+// has made irrelevant.
 constexpr int kSpill = kPStack / 2;
 // (inlined: as real calls the two slow paths cost 4 % -- ABI constraints on the hot loop)
 constexpr uint32_t kStackStride = kTraceThreads * 8u;
@@ -215,7 +225,15 @@ __device__ __forceinline__ void sstack_st(uint32_t saddr, int i, uint32_t ref, u
 __device__ __forceinline__ void sstack_ld(uint32_t saddr, int i, uint32_t& ref, uint32_t& tb) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(saddr + (uint32_t)i * kStackStride) : "memory");
 }
-__device__ __forceinline__ void sstack_reset(uint2* ovf, int& sp) { sp = 0; ovf[0].x = 0u; }
+template <bool SENTINEL = false>
+__device__ __forceinline__ void sstack_reset(uint32_t saddr, uint2* ovf, int& sp) {
+    sp = 0;
+    if (SENTINEL) {
+        sstack_st(saddr, 0, kDone, 0xff800000u);  // "finished", entry distance -inf (never culled)
+        sp = 1;
+    }
+    ovf[0].x = 0u;
+}
 // (sp by value in and out: a reference parameter of a real call would pin sp to local memory)
 static __device__ __forceinline__ int sstack_spill(uint32_t saddr, uint2* ovf, int sp) {
     const uint32_t n = ovf[0].x;
@@ -242,7 +260,10 @@ static __device__ __forceinline__ int sstack_unspill(uint32_t saddr, uint2* ovf)
     ovf[0].x = n - kSpill;
     return kSpill;
 }
-// pop until an entry that can still beat `bound` (or the stack is empty -> kDone)
+// pop until an entry that can still beat `bound` (the sentinel always does -> kDone)
+// (tried: peeling the first pop and draining four entries per shared-memory round trip after a dead
+// one -- the drain is 17 % of the stall samples at 3..6 lanes -- but the window's registers spill in a
+// 64-register kernel: 8.4 -> 9.3 (window 2) .. 13.9 ms (window 8), profiles/r2_sweeps.txt)
 __device__ __forceinline__ uint32_t sstack_pop_live(uint32_t saddr, uint2* ovf, int& sp, float bound) {
     while (true) {
         if (sp == 0) {

@@ -48,7 +48,6 @@ struct prt_ctx {
     uint32_t* flag_list[kFlagRing] = {};
     unsigned int* flag_count = nullptr;  // [kFlagRing]
     uint64_t flag_cap[kFlagRing] = {};
-    unsigned flag_next = 0;
     static constexpr unsigned kFetchRing = 32;
     unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
     unsigned fetch_next = 0;
@@ -120,8 +119,10 @@ enum { PROF_RAYGEN = 0, PROF_CLOSEST = 1, PROF_SHADE = 2, PROF_SHADOW = 3, PROF_
 void prof_begin(prt_ctx* ctx, int cls, cudaStream_t stream, int launches = 1);
 void prof_end(prt_ctx* ctx, cudaStream_t stream);
 // traverse.cu
+// flag_slot: which (flag list, flag count) pair an EXACT launch uses; launches that may overlap on
+// different streams (the host-buffer pipeline) take different slots
 int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* out0, void* out1,
-                 uint32_t flags, cudaStream_t stream);
+                 uint32_t flags, cudaStream_t stream, unsigned flag_slot = 0);
 // bvh_build.cu
 int build_bvh(prt_ctx* ctx, const prt_bvh_options* opts, prt_bvh_stats* stats);
 // wavefront.cu

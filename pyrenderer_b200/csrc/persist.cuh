@@ -151,7 +151,7 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                     bt = tmax; bu = 0.f; bv = 0.f; bgid = -1;
                     bdt = 0.f; flagged = false;
                     cur = 0;
-                    sstack_reset(ovf, sp);
+                    sstack_reset<EXACT>(saddr, ovf, sp);
                     has_ray = true;
                     if (COUNT) ++c_rays;
                 }

@@ -367,7 +367,7 @@ int prt_trace_closest_host(prt_ctx* ctx, const prt_ray* rays_host, uint64_t n, p
         PRT_CUDA_TRY(ctx, cudaEventRecord(uploaded, s_up));
         PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_tr, uploaded, 0));
         if (i >= (uint64_t)S) PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_tr, downloaded, 0));  // hit slot drained
-        rc = launch_trace(ctx, 0, (const float4*)(dr + off), m, dh + off, nullptr, flags, s_tr);
+        rc = launch_trace(ctx, 0, (const float4*)(dr + off), m, dh + off, nullptr, flags, s_tr, (unsigned)slot);
         if (rc != PRT_OK) break;
         PRT_CUDA_TRY(ctx, cudaEventRecord(traced, s_tr));
         PRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s_down, traced, 0));

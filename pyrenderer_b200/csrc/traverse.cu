@@ -193,7 +193,7 @@ static void launch1(bool exact, bool count, bool brute, dim3 grid, cudaStream_t 
 }
 
 int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* out0, void* out1,
-                 uint32_t flags, cudaStream_t stream) {
+                 uint32_t flags, cudaStream_t stream, unsigned flag_slot) {
     if (n == 0) return PRT_OK;
     if (n > (1ull << 31)) { ctx->set_error("trace: n=%llu exceeds 2^31 rays per call", (unsigned long long)n); return PRT_ERR_INVALID; }
     bool exact = flags & PRT_TRACE_EXACT, count = flags & PRT_TRACE_COUNT, brute = flags & PRT_TRACE_BRUTE;
@@ -203,7 +203,7 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
     uint32_t* flag_list = nullptr;
     unsigned int* flag_count = nullptr;
     if (exact) {  // grow-only flag list of this launch's ring slot (worst case: every ray flagged)
-        const unsigned slot = ctx->flag_next++ % prt_ctx::kFlagRing;
+        const unsigned slot = flag_slot % prt_ctx::kFlagRing;
         if (ctx->flag_cap[slot] < n) {
             PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());  // an earlier launch (any stream) may still use the old list
             cudaFree(ctx->flag_list[slot]);

@@ -70,7 +70,7 @@ __device__ __forceinline__ void trace_one(const SceneDev& sc, float4 ro, float4 
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
     uint2 ovf[kPStackOvf];
     int sp;
-    sstack_reset(ovf, sp);
+    sstack_reset(saddr, ovf, sp);
     uint32_t cur = 0;
     while (cur != kDone) {
         // EXACT: a candidate closer than best + its error bound must still be visited
@@ -142,7 +142,7 @@ __device__ __forceinline__ void trace_one_f64(const SceneDev& sc, float4 ro, flo
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stack_col);
     uint2 ovf[kPStackOvf];
     int sp;
-    sstack_reset(ovf, sp);
+    sstack_reset(saddr, ovf, sp);
     uint32_t cur = 0;
     while (cur != kDone) {
         // box culling stays FP32 but conservative: bound rounded up, intervals widened (EXACT)

@@ -325,6 +325,23 @@ def test_edge_cases(gpu_ctx, cornell):
     rays = make_rays(o, d.astype(np.float32), tmin=1e-5, tmax=99999.9)
     check_against_oracle(gpu_ctx, a["tris"], rays, EXACT, "cornell-edges")
     check_against_oracle(gpu_ctx, a["tris"], rays, EXACT | BRUTE, "cornell-edges-brute")
+    # axis-parallel rays whose zero components are NEGATIVE zeros (e.g. the product -1 * 0.0): the slab
+    # test's octant must follow the sign of the clamped reciprocal (-1e20), or near and far planes swap
+    # and a ray travelling inside a slab misses every box
+    n = rays.shape[0] // 3
+    rz = rays[0::3][:n].copy()   # the (0, 0, -1) family
+    rz[:, 4] = -0.0
+    rz[:, 5] = -0.0
+    ry = rays[1::3][:n].copy()   # the (0, 1, 0) family, origins on the floor
+    ry[:, 4] = -0.0
+    ry[:, 6] = -0.0
+    neg = np.concatenate([rz, ry])
+    assert np.all(np.signbit(neg[:, 4]))
+    ref = oracle.closest_hit(a["tris"], neg)
+    assert np.mean(ref[0] >= 0) > 0.9
+    check_against_oracle(gpu_ctx, a["tris"], neg, EXACT, "negative-zero-directions", ref)
+    ids_f, _, _, _ = gpu_closest(gpu_ctx, neg, 0)
+    assert np.mean(ids_f != ref[0]) < 0.02  # plain FP32: these rays run along the quads' shared edges
 
 
 def test_host_buffer_entry_point(gpu_ctx):
