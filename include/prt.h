@@ -242,6 +242,23 @@ typedef struct {
 int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity, uint32_t* count_dev);
 /* same with a HOST accumulation buffer (upload, render, download; synchronous) */
 int prt_render_host(prt_ctx* ctx, const prt_render_params* params, float* accum_host);
+/* Known-answer hook for the specular BSDF device functions that the shade kernel calls
+ * (core/bsdf_taichi.py:6-22 reflectance / reflect / refract, :45-86 Metal.scatter / Dielectric.scatter,
+ * mathematics/vec3_taichi.py:33-39 random_in_unit_sphere): for every query, the un-normalised
+ * scattered direction and a validity flag, wi_valid_dev[i] = (wi.x, wi.y, wi.z, 1 or 0).
+ * d = incoming direction (any length), ns = shading normal on the incoming side, type = PRT_MAT_MIRROR /
+ * _DIELECTRIC / _CONDUCTOR, u = uniforms in the order the reference draws them. */
+typedef struct {
+    float d[3];
+    uint32_t type;
+    float ns[3];
+    uint32_t front; /* dielectric: 1 = entering (ratio 1/ior) */
+    float ior, roughness;
+    float u[3];
+    uint32_t pad[3];
+} prt_bsdf_query; /* 64 bytes */
+int prt_eval_specular(prt_ctx* ctx, const prt_bsdf_query* queries_dev, uint64_t n, float* wi_valid_dev, void* stream);
+
 /* Device memory is grow-only: scene, BVH, build scratch, staging and wavefront buffers are kept and
  * reused by later calls (a rebuild or a new scene of the same size allocates nothing).  This frees
  * everything that is scratch (build arena, host-call staging, exact-mode flag lists, wavefront

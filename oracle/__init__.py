@@ -157,6 +157,41 @@ def cosine_sample_hemisphere(n, u1, u2):
     return out
 
 
+def schlick(cosine, idx):
+    lib().orc_schlick.restype = C.c_double
+    return float(lib().orc_schlick(C.c_double(cosine), C.c_double(idx)))
+
+
+def reflect(v, n):
+    v, n = (np.ascontiguousarray(x, dtype=np.float64) for x in (v, n))
+    out = np.zeros(3)
+    lib().orc_reflect(_p(v, C.c_double), _p(n, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def refract(v, n, eta):
+    v, n = (np.ascontiguousarray(x, dtype=np.float64) for x in (v, n))
+    out = np.zeros(3)
+    lib().orc_refract(_p(v, C.c_double), _p(n, C.c_double), C.c_double(eta), _p(out, C.c_double))
+    return out
+
+
+def in_unit_sphere(ua, ub, uc):
+    out = np.zeros(3)
+    lib().orc_in_unit_sphere(C.c_double(ua), C.c_double(ub), C.c_double(uc), _p(out, C.c_double))
+    return out
+
+
+def scatter_specular(kind, d, ns, front=True, ior=1.5, roughness=0.0, u=(0.5, 0.5, 0.5)):
+    """(valid, wi un-normalised) of the oracle's specular sampler (kind: 2 mirror, 3 dielectric, 4 conductor)."""
+    d, ns = (np.ascontiguousarray(x, dtype=np.float64) for x in (d, ns))
+    out = np.zeros(3)
+    ok = lib().orc_scatter_specular(C.c_uint32(kind), _p(d, C.c_double), _p(ns, C.c_double), C.c_int(1 if front else 0),
+                                    C.c_double(ior), C.c_double(roughness), C.c_double(u[0]), C.c_double(u[1]),
+                                    C.c_double(u[2]), _p(out, C.c_double))
+    return bool(ok), out
+
+
 def make_camera(iview, sensor_w, sensor_h, focal, width, height, aperture=0.0):
     cam = Camera()
     iv = np.ascontiguousarray(iview, dtype=np.float64).reshape(16)

@@ -481,6 +481,43 @@ static inline void in_unit_sphere(double ua, double ub, double uc, double* out) 
     out[2] = r * cos(phi);
 }
 
+/* Specular scattering, semantics of core/bsdf_taichi.py:45-86.  `d` = incoming direction (any
+ * length), `ns` = shading normal facing the incoming side.  type 2 = mirror (Metal, roughness 0),
+ * 4 = conductor (Metal.scatter :54-60: reflect(unit d, n) + roughness * random_in_unit_sphere(),
+ * valid only if it leaves on the normal's side), 3 = dielectric (Dielectric.scatter :71-86: ratio =
+ * 1/ior on the front side, else ior; total internal reflection or Schlick > u1 reflects, else
+ * refracts).  (u1, u2, u3) = the uniforms in the order the reference draws them (conductor: theta,
+ * v, r of the sphere sample; dielectric: the Fresnel draw).  wi_out is NOT normalised (the
+ * reference returns out_direction as is); returns 1 if the sample is valid. */
+int orc_scatter_specular(uint32_t type, const double d[3], const double ns[3], int front, double ior,
+                         double roughness, double u1, double u2, double u3, double wi_out[3]) {
+    double ud[3] = {d[0], d[1], d[2]};
+    normalize3(ud);
+    if (type == 2) {
+        reflect3(ud, ns, wi_out);
+        return 1;
+    }
+    if (type == 4) {
+        double f[3];
+        reflect3(ud, ns, wi_out);
+        in_unit_sphere(u1, u2, u3, f);
+        for (int k = 0; k < 3; ++k) wi_out[k] += roughness * f[k];
+        return dot3(wi_out, ns) > 0.0; /* bsdf_taichi.py:58 */
+    }
+    double ratio = front ? 1.0 / ior : ior;
+    double ct = -dot3(ud, ns);
+    if (ct > 1.0) ct = 1.0;
+    double st = sqrt(1.0 - ct * ct);
+    if (ratio * st > 1.0 || schlick(ct, ratio) > u1) reflect3(ud, ns, wi_out);
+    else refract3(ud, ns, ratio, wi_out);
+    return 1;
+}
+/* exported for the known-answer tests against the reference's own functions (tests/golden/radiance_golden.npz) */
+double orc_schlick(double cosine, double idx) { return schlick(cosine, idx); }
+void orc_reflect(const double v[3], const double n[3], double out[3]) { reflect3(v, n, out); }
+void orc_refract(const double v[3], const double n[3], double eta, double out[3]) { refract3(v, n, eta, out); }
+void orc_in_unit_sphere(double ua, double ub, double uc, double out[3]) { in_unit_sphere(ua, ub, uc, out); }
+
 /* ---- integrator (core/tracing.py:116-155) ------------- */
 typedef struct {
     soup_t soup;
@@ -544,28 +581,11 @@ static void trace_path(const scene_t* sc, const orc_render_params* P, uint32_t p
              * shading normal faces the incoming side */
             double ns[3] = {n[0], n[1], n[2]};
             if (!front && !m->two_sided) { ns[0] = -n[0]; ns[1] = -n[1]; ns[2] = -n[2]; }
-            double ud[3] = {d[0], d[1], d[2]};
-            normalize3(ud);
             uint32_t r2[4];
             rng4(P->seed, pixel, sample, bounce, 2, r2);
-            int ok = 1;
-            if (m->type == 2) {
-                reflect3(ud, ns, wi);
-            } else if (m->type == 4) {
-                double f[3];
-                reflect3(ud, ns, wi);
-                in_unit_sphere(u24(r1[0]), u24(r1[1]), u24(r2[2]), f);
-                for (int k = 0; k < 3; ++k) wi[k] += (double)m->roughness * f[k];
-                ok = dot3(wi, ns) > 0.0; /* bsdf_taichi.py:58 */
-            } else {
-                double ratio = front ? 1.0 / (double)m->ior : (double)m->ior;
-                double ct = -dot3(ud, ns);
-                if (ct > 1.0) ct = 1.0;
-                double st = sqrt(1.0 - ct * ct);
-                if (ratio * st > 1.0 || schlick(ct, ratio) > u24(r1[0])) reflect3(ud, ns, wi);
-                else refract3(ud, ns, ratio, wi);
-            }
-            if (!ok) break;
+            if (!orc_scatter_specular(m->type, d, ns, front, (double)m->ior, (double)m->roughness, u24(r1[0]),
+                                      u24(r1[1]), u24(r2[2]), wi))
+                break;
             normalize3(wi);
             for (int k = 0; k < 3; ++k) beta[k] *= (double)m->albedo[k];
         }

@@ -18,6 +18,9 @@ MATERIAL_DTYPE = np.dtype(
     [("albedo", "<f4", 3), ("type", "<u4"), ("ior", "<f4"), ("roughness", "<f4"),
      ("two_sided", "<u4"), ("pad", "<u4"), ("emission", "<f4", 3), ("pad2", "<u4")])
 assert MATERIAL_DTYPE.itemsize == 48
+BSDF_QUERY_DTYPE = np.dtype([("d", "<f4", 3), ("type", "<u4"), ("ns", "<f4", 3), ("front", "<u4"), ("ior", "<f4"),
+                             ("roughness", "<f4"), ("u", "<f4", 3), ("pad", "<u4", 3)])
+assert BSDF_QUERY_DTYPE.itemsize == 64
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 
 TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE = 1, 2, 4
@@ -73,6 +76,7 @@ EXPORTS = [
     "prt_render_host", "prt_set_wave_paths", "prt_set_path_log", "prt_get_counters", "prt_reset_counters",
     "prt_synchronize", "prt_comm_unique_id", "prt_comm_init", "prt_comm_attach", "prt_comm_destroy", "prt_comm_info",
     "prt_allreduce_sum", "prt_render_sharded", "prt_profile_begin", "prt_profile_end", "prt_release_scratch",
+    "prt_eval_specular",
 ]
 
 
@@ -123,6 +127,7 @@ def load():
     lib.prt_allreduce_sum.argtypes = [vp, vp, u64, vp]
     lib.prt_render_sharded.argtypes = [vp, C.POINTER(PrtRenderParams), vp, vp]
     lib.prt_release_scratch.argtypes = [vp]
+    lib.prt_eval_specular.argtypes = [vp, vp, u64, vp, vp]
     lib.prt_profile_begin.argtypes = [vp]
     lib.prt_profile_end.argtypes = [vp, C.POINTER(PrtKernelTimes)]
     for name in EXPORTS:
@@ -283,6 +288,11 @@ class Context:
     def render_host(self, params, accum):
         assert accum.dtype == np.float32 and accum.flags.c_contiguous
         self._check(self.lib.prt_render_host(self.h, C.byref(params), _np_ptr(accum)))
+
+    def eval_specular(self, queries_dev, n, out_dev, stream=None):
+        """queries_dev: device buffer of n BSDF_QUERY_DTYPE records; out_dev: torch f32 [n, 4] (wi, valid)."""
+        self._check(self.lib.prt_eval_specular(self.h, _dev_ptr(queries_dev), int(n), _dev_ptr(out_dev),
+                                               _stream_ptr(stream, self.device)))
 
     def release_scratch(self):
         self._check(self.lib.prt_release_scratch(self.h))

@@ -131,4 +131,5 @@ int generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int jit
 int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim_ids,
            cudaStream_t stream, const float4* user_rays = nullptr, uint64_t n_user = 0);
 void wavefront_free(prt_ctx* ctx);
+int eval_specular(prt_ctx* ctx, const prt_bsdf_query* q, uint64_t n, float* out, cudaStream_t stream);
 }  // namespace prt

@@ -439,6 +439,13 @@ int prt_set_path_log(prt_ctx* ctx, prt_segment* segments_dev, uint64_t capacity,
     return PRT_OK;
 }
 
+int prt_eval_specular(prt_ctx* ctx, const prt_bsdf_query* queries_dev, uint64_t n, float* wi_valid_dev, void* stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (n && (!queries_dev || !wi_valid_dev)) { ctx->set_error("eval_specular: NULL buffer"); return PRT_ERR_INVALID; }
+    return eval_specular(ctx, queries_dev, n, wi_valid_dev, (cudaStream_t)stream);
+}
+
 int prt_release_scratch(prt_ctx* ctx) {
     CHECK_CTX(ctx);
     USE_DEVICE(ctx);

@@ -103,4 +103,29 @@ __device__ __forceinline__ float3 in_unit_sphere(float ua, float ub, float uc) {
     return make_float3(r * sp * ct, r * sp * st, r * cp);
 }
 
+// Specular scattering, core/bsdf_taichi.py:45-86 (the oracle's orc_scatter_specular in FP32): `d` =
+// incoming direction (any length), `ns` = shading normal on the incoming side; PRT_MAT_MIRROR =
+// Metal with roughness 0, PRT_MAT_CONDUCTOR = Metal.scatter (:54-60, valid only if the fuzzed
+// direction leaves on the normal's side), PRT_MAT_DIELECTRIC = Dielectric.scatter (:71-86).  wi is
+// NOT normalised.  (u1, u2, u3): conductor = theta, v, r of random_in_unit_sphere; dielectric = u1 is
+// the Fresnel draw.  shade_kernel and the known-answer entry point prt_eval_specular both call this.
+__device__ __forceinline__ bool sample_specular(uint32_t type, float3 d, float3 ns, bool front, float ior,
+                                                float roughness, float u1, float u2, float u3, float3& wi) {
+    const float3 ud = normalize_fast(d);
+    if (type == PRT_MAT_MIRROR) {
+        wi = reflect(ud, ns);
+        return true;
+    }
+    if (type == PRT_MAT_CONDUCTOR) {
+        wi = reflect(ud, ns) + in_unit_sphere(u1, u2, u3) * roughness;
+        return dot(wi, ns) > 0.0f;  // core/bsdf_taichi.py:58
+    }
+    const float ratio = front ? 1.0f / ior : ior;
+    const float ct = fminf(-dot(ud, ns), 1.0f);
+    const float st = sqrtf(1.0f - ct * ct);
+    if (ratio * st > 1.0f || schlick(ct, ratio) > u1) wi = reflect(ud, ns);
+    else wi = refract(ud, ns, ratio);
+    return true;
+}
+
 }  // namespace prt

@@ -346,20 +346,9 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
                     } else {
                         pdf_prev = -1.0f;
                         float3 ns = (!front && !m.two_sided) ? -n : n;
-                        float3 ud = normalize_fast(d);
-                        if (m.type == PRT_MAT_MIRROR) {
-                            wi = reflect(ud, ns);
-                        } else if (m.type == PRT_MAT_CONDUCTOR) {
-                            uint4 r2 = rng4(P.seed, pixel, s, bounce, 2);
-                            wi = reflect(ud, ns) + in_unit_sphere(u24(r1.x), u24(r1.y), u24(r2.z)) * m.roughness;
-                            ok = dot(wi, ns) > 0.0f;  // core/bsdf_taichi.py:58
-                        } else {
-                            float ratio = front ? 1.0f / m.ior : m.ior;
-                            float ct = fminf(-dot(ud, ns), 1.0f);
-                            float st = sqrtf(1.0f - ct * ct);
-                            if (ratio * st > 1.0f || schlick(ct, ratio) > u24(r1.x)) wi = reflect(ud, ns);
-                            else wi = refract(ud, ns, ratio);
-                        }
+                        float u3 = 0.0f;
+                        if (m.type == PRT_MAT_CONDUCTOR) u3 = u24(rng4(P.seed, pixel, s, bounce, 2).z);
+                        ok = sample_specular(m.type, d, ns, front, m.ior, m.roughness, u24(r1.x), u24(r1.y), u3, wi);
                         if (ok) {
                             wi = normalize_fast(wi);
                             b = b * alb;
@@ -464,6 +453,24 @@ __global__ void accumulate_kernel(const float4* __restrict__ L, uint32_t npix, u
     }
     float4 a = accum[pixel];
     accum[pixel] = make_float4(a.x + s.x, a.y + s.y, a.z + s.z, a.w + (float)ns_wave);
+}
+
+// known-answer hook: the production specular sampler on caller-supplied inputs
+__global__ void eval_specular_kernel(const prt_bsdf_query* __restrict__ q, uint64_t n, float4* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const prt_bsdf_query a = q[i];
+    float3 wi = make_float3(0.f, 0.f, 0.f);
+    const bool ok = sample_specular(a.type, make_float3(a.d[0], a.d[1], a.d[2]), make_float3(a.ns[0], a.ns[1], a.ns[2]),
+                                    a.front != 0u, a.ior, a.roughness, a.u[0], a.u[1], a.u[2], wi);
+    out[i] = make_float4(wi.x, wi.y, wi.z, ok ? 1.0f : 0.0f);
+}
+
+int eval_specular(prt_ctx* ctx, const prt_bsdf_query* q, uint64_t n, float* out, cudaStream_t stream) {
+    if (n == 0) return PRT_OK;
+    eval_specular_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(q, n, (float4*)out);
+    PRT_CUDA_TRY(ctx, cudaGetLastError());
+    return PRT_OK;
 }
 
 static CamDev cam_dev(const prt_camera& c) {

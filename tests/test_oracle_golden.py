@@ -1,10 +1,12 @@
 """The CPU oracle (oracle/pt_oracle.c) against fixtures produced by the
 REFERENCE's own code (tests/golden/make_golden.py).  No GPU needed."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle
-from conftest import make_rays
+from conftest import GOLDEN, make_rays
 
 F32MAX = 3.4028234663852886e+38
 
@@ -129,3 +131,79 @@ def test_golden_path_of_reference_test_py(golden, cornell):
     # row k+1 starts where row k ended
     for k in range(8):
         assert np.allclose(gp[k, 1:4] + t[k] * gp[k, 4:7], gp[k + 1, 1:4], atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# radiance + specular BSDFs: fixtures composed from the reference's own functions
+# (tests/golden/make_radiance_golden.py)
+RADIANCE = os.path.join(os.path.dirname(GOLDEN), "radiance_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def rad_golden():
+    return np.load(RADIANCE)
+
+
+def test_radiance_matches_the_reference_composed_path_tracer(rad_golden):
+    """Per-path radiance of a 32x32x4-spp Cornell render traced by a path tracer composed of the
+    reference's imported functions (numba Moller-Trumbore, compute_pos, Camera.generate_ray,
+    samplers_debug.cosine_sample_hemisphere, shapes2 sample_a_point) under the estimator of
+    core/tracing.py:116-155: oracle.render reproduces every path to 1e-12 and every primary id."""
+    g = rad_golden
+    W, H, SPP, DEPTH, SEED = (int(x) for x in g["params"])
+    mats = np.ascontiguousarray(g["materials"]).view(oracle.MATERIAL_DTYPE).reshape(-1)
+    from pyrenderer_b200.core.camera import Camera
+    cam = Camera([0, 1, 6.8], [0, 1, 0], [0, 1, 0], [W, H], fov=19.5)
+    iview, sw, sh, focal, _, _ = cam.device_record()
+    assert np.allclose(iview.reshape(4, 4), g["cam_iview"], rtol=0, atol=1e-15)
+    ocam = oracle.make_camera(iview, sw, sh, focal, W, H)
+    rays = oracle.generate_rays(ocam, seed=SEED, s0=0, s1=SPP, jitter=True)
+    assert np.array_equal(rays[..., [0, 1, 2, 4, 5, 6]].view(np.uint32), g["rays"].view(np.uint32)), "camera rays differ"
+    worst = 0.0
+    for s in range(SPP):
+        acc, ids, _ = oracle.render(g["tris"], g["normals"], g["tri_material"], mats, g["light_tris"], ocam,
+                                    oracle.make_params(seed=SEED, spp_begin=s, spp_end=s + 1, max_depth=DEPTH), want_ids=True)
+        assert np.array_equal(ids[..., 0], g["prim_ids"][..., s])
+        ref = g["radiance"][:, :, s, :]
+        err = np.abs(acc[..., :3] - ref).max() / np.abs(ref).max()
+        worst = max(worst, float(err))
+    print(f"[radiance] oracle vs reference-composed path tracer: max rel err {worst:.2e} over {W * H * SPP} paths")
+    assert worst < 1e-12
+    assert g["radiance"].mean() > 0.05 and np.mean(g["radiance"].sum(axis=-1) > 0) > 0.8
+
+
+def test_specular_bsdfs_match_bsdf_taichi(rad_golden):
+    """Schlick reflectance, reflect, refract, random_in_unit_sphere, Metal.scatter and
+    Dielectric.scatter of core/bsdf_taichi.py / mathematics/vec3_taichi.py, run from the reference's
+    source (taichi names bound to plain Python), against the oracle's functions."""
+    g = rad_golden
+    for i, c in enumerate(g["schlick_cos"]):
+        for j, e in enumerate(g["schlick_idx"]):
+            assert abs(oracle.schlick(c, e) - g["schlick_val"][i, j]) <= 1e-15
+    # analytic anchors: normal incidence r0 = ((1-n)/(1+n))^2 (glass: 0.04), grazing incidence 1
+    assert abs(oracle.schlick(1.0, 1.5) - 0.04) < 1e-15 and abs(oracle.schlick(0.0, 1.5) - 1.0) < 1e-15
+    for k in range(g["spec_v"].shape[0]):
+        v, n, eta = g["spec_v"][k], g["spec_n"][k], float(g["spec_eta"][k])
+        assert np.abs(oracle.reflect(v, n) - g["reflect_res"][k]).max() <= 1e-15
+        assert np.abs(oracle.refract(v, n, eta) - g["refract_res"][k]).max() <= 1e-14
+        assert np.abs(oracle.in_unit_sphere(*g["sphere_u"][k]) - g["sphere_res"][k]).max() <= 1e-15
+        d = v * g["metal_scale"][k]
+        ok, wi = oracle.scatter_specular(4, d, n, roughness=float(g["metal_rough"][k]), u=g["sphere_u"][k])
+        assert ok == bool(g["metal_ok"][k]) and np.abs(wi - g["metal_res"][k]).max() <= 1e-14
+        ok, wi = oracle.scatter_specular(3, d, n, front=bool(g["diel_front"][k]), ior=float(g["diel_ior"][k]),
+                                         u=(float(g["diel_u"][k]), 0.0, 0.0))
+        assert ok and np.abs(wi - g["diel_res"][k]).max() <= 1e-14
+        ok, wi = oracle.scatter_specular(2, d, n)  # mirror == Metal with roughness 0
+        assert ok and np.abs(wi - g["reflect_res"][k]).max() <= 1e-14
+    # the laws the functions stand for: reflection keeps the length and flips the normal component;
+    # refraction obeys Snell (sin_t = eta sin_i) wherever it is not total internal reflection
+    v, n, eta = g["spec_v"], g["spec_n"], g["spec_eta"]
+    r = g["reflect_res"]
+    assert np.allclose(np.linalg.norm(r, axis=1), 1.0, atol=1e-14) and np.allclose(np.sum(r * n, 1), -np.sum(v * n, 1), atol=1e-14)
+    cos_i = -np.sum(v * n, 1)
+    sin_i = np.sqrt(1 - cos_i ** 2)
+    ok = eta * sin_i < 1.0
+    t = g["refract_res"][ok]
+    sin_t = np.linalg.norm(t - np.sum(t * n[ok], 1)[:, None] * n[ok], axis=1)
+    assert np.allclose(sin_t, eta[ok] * sin_i[ok], atol=1e-13) and np.allclose(np.linalg.norm(t, axis=1), 1.0, atol=1e-13)
+    assert np.all(np.sum(t * n[ok], 1) < 0)
