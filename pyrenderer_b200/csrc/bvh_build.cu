@@ -259,6 +259,7 @@ struct TreeletShared {
     uint32_t pk[kTreelet];                    // per position of the current range: bin per axis, 8 bits each
     int names[kTreelet];                      // internal node names available to this subtree; [0] = root
     int stack[kTreelet][3];                   // begin, end, name
+    int bins[3][16][8];                       // per (axis, bin): ordered-int box lo.xyz, hi.xyz, count, pad
 };
 
 __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
@@ -266,8 +267,8 @@ __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
     return 2.0f * (x * y + y * z + z * x);
 }
 
-// Best binned-SAH plane of order[b, e) with NB bins per axis.  Lane (axis, bin) scans the range and
-// keeps its bin's box in registers; prefix / suffix unions over the NB bins of an axis are shuffle
+// Best binned-SAH plane of order[b, e) with NB bins per axis.  The bin boxes are accumulated in shared
+// memory, lane (axis, bin) then takes its bin's box into registers; prefix / suffix unions over the NB bins of an axis are shuffle
 // scans inside an NB-lane group; candidate plane j = "bins <= j go left".  NB = 16: two rounds
 // (axes x,y then z); NB = 8: the 24 (axis, bin) pairs fit one round.  Returns cost (inf: none).
 template <int NB>
@@ -279,15 +280,33 @@ __device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int
     constexpr int kRounds = NB == 16 ? 2 : 1;
     float best = inf;
     best_slot = -1;
-    // bins of every triangle of the range, one triangle per lane
+    // Bin boxes by shared-memory atomics on order-preserving ints (min / max do not depend on the order
+    // of arrival, so the result is the same as a scan): one triangle per lane and step.  (Round 1 had
+    // every (axis, bin) lane scan the whole range for its members -- 32 x c loop trips for c useful
+    // ones, the bulk of the 0.9 ms the treelets took at 1M triangles.)
+    for (int k = lane; k < 3 * NB; k += 32) {
+        int* bb = S.bins[k / NB][k % NB];
+        bb[0] = bb[1] = bb[2] = 0x7fffffff;              // f2ord(+inf) <= this
+        bb[3] = bb[4] = bb[5] = (int)0x80000000;
+        bb[6] = 0;
+    }
+    __syncwarp();
     for (int k = b + lane; k < e; k += 32) {
         const int q = S.order[k];
         uint32_t pk = 0;
+        const int l0 = f2ord(S.lo[q][0]), l1 = f2ord(S.lo[q][1]), l2 = f2ord(S.lo[q][2]);
+        const int h0 = f2ord(S.hi[q][0]), h1 = f2ord(S.hi[q][1]), h2 = f2ord(S.hi[q][2]);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             int j = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cmin[a]) * scale[a]);
             j = j > NB - 1 ? NB - 1 : j;
             pk |= (uint32_t)j << (8 * a);
+            if (scale[a] > 0.0f) {
+                int* bb = S.bins[a][j];
+                atomicMin(bb + 0, l0); atomicMin(bb + 1, l1); atomicMin(bb + 2, l2);
+                atomicMax(bb + 3, h0); atomicMax(bb + 4, h1); atomicMax(bb + 5, h2);
+                atomicAdd(bb + 6, 1);
+            }
         }
         S.pk[k] = pk;
     }
@@ -299,15 +318,11 @@ __device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int
         float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
         int cnt = 0;
         if (sc_a > 0.0f) {
-            const uint32_t want = (uint32_t)bin << (8 * a), mask = 0xffu << (8 * a);
-#pragma unroll 4
-            for (int k = b; k < e; ++k) {
-                if ((S.pk[k] & mask) == want) {
-                    const int q = S.order[k];
-                    l0 = fminf(l0, S.lo[q][0]); l1 = fminf(l1, S.lo[q][1]); l2 = fminf(l2, S.lo[q][2]);
-                    h0 = fmaxf(h0, S.hi[q][0]); h1 = fmaxf(h1, S.hi[q][1]); h2 = fmaxf(h2, S.hi[q][2]);
-                    ++cnt;
-                }
+            const int* bb = S.bins[a][bin];
+            cnt = bb[6];
+            if (cnt > 0) {
+                l0 = ord2f(bb[0]); l1 = ord2f(bb[1]); l2 = ord2f(bb[2]);
+                h0 = ord2f(bb[3]); h1 = ord2f(bb[4]); h2 = ord2f(bb[5]);
             }
         }
         // inclusive prefix (bins 0..bin) and suffix (bins bin..NB-1) within the NB-lane group
@@ -335,12 +350,13 @@ __device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int
             if (cost < best) { best = cost; best_slot = a * NB + bin; }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(FULL, best, o);
-        const int os = __shfl_xor_sync(FULL, best_slot, o);
-        if (ob < best || (ob == best && os >= 0 && (best_slot < 0 || os < best_slot))) { best = ob; best_slot = os; }
-    }
-    return best;
+    // lowest cost, lowest slot among equal costs: two warp reductions (costs are >= 0 or +inf, so their
+    // bit patterns order like unsigned integers)
+    const unsigned key = __float_as_uint(best);
+    const unsigned kmin = __reduce_min_sync(FULL, key);
+    const int smin = __reduce_min_sync(FULL, (key == kmin && best_slot >= 0) ? best_slot : 0x7fffffff);
+    best_slot = smin == 0x7fffffff ? -1 : smin;
+    return __uint_as_float(kmin);
 }
 
 __global__ void __launch_bounds__(32 * kTreeletWarps)
@@ -406,11 +422,10 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                     }
                 }
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-                    for (int o = 16; o > 0; o >>= 1) {
-                        cmin[a] = fminf(cmin[a], __shfl_xor_sync(FULL, cmin[a], o));
-                        cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(FULL, cmax[a], o));
-                    }
+                for (int a = 0; a < 3; ++a) {  // warp min / max through order-preserving ints (REDUX)
+                    cmin[a] = ord2f(__reduce_min_sync(FULL, f2ord(cmin[a])));
+                    cmax[a] = ord2f(__reduce_max_sync(FULL, f2ord(cmax[a])));
+                }
                 // 16 bins for the large ranges near the treelet root, 8 (one round) below
                 const int nb = c > 32 ? 16 : 8;
                 float scale[3];
@@ -889,7 +904,7 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[sorted], keys_hi, n, B.left, B.right, B.parent, B.range);
     if (n > 2 && opt.treelets) {
         treelet_roots_kernel<<<gN, T>>>(B.range, B.parent, n, B.roots, B.n_roots);
-        treelet_sah_kernel<<<ctx->num_sms * 8, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
+        treelet_sah_kernel<<<ctx->num_sms * 7, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
                                                                    B.parent, n, B.roots, B.n_roots);
     }
     cudaEventRecord(ev[3]);

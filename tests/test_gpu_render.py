@@ -215,7 +215,9 @@ def test_specular_materials_against_oracle(gpu_ctx, cornell):
     err = rel_rmse(acc_g[..., :3], acc_o[..., :3])
     print(f"[specular] rel RMSE {err:.3e} (GPU vs oracle, equal seed, 32 spp, depth 8)")
     assert np.isfinite(acc_g).all()
-    assert err < 2e-2  # specular chains amplify FP32-vs-FP64 path divergence
+    # measured 2.2e-3 (gpurun r2-26); specular chains amplify FP32-vs-FP64 path divergence: a path whose
+    # Fresnel draw or fuzzed direction lands on the other side of a branch carries a different radiance
+    assert err < 7e-3
 
 
 def test_python_entry_points(cornell):
@@ -404,9 +406,10 @@ def test_gpu_against_the_reference_composed_radiance(gpu_ctx):
     img_err = rel_rmse(got.sum(axis=2), ref.sum(axis=2))
     print(f"[reference radiance] {W * H * SPP} paths: median |dL| / max L = {np.median(per_path):.1e}, "
           f"paths off by > 1e-4: {frac_off:.2e}, image rel RMSE {img_err:.2e}")
-    assert np.median(per_path) < 1e-6
-    assert frac_off < 1e-2
-    assert img_err < 1e-3
+    # measured (gpurun r2-26): median 1.2e-8, 1 path of 4096 off by more than 1e-4, image 1.1e-5
+    assert np.median(per_path) < 1e-7
+    assert frac_off < 1e-3
+    assert img_err < 1e-4
 
 
 def test_specular_device_functions_against_bsdf_taichi(gpu_ctx):
@@ -443,4 +446,4 @@ def test_specular_device_functions_against_bsdf_taichi(gpu_ctx):
     print(f"[specular device fns] max |wi - reference| mirror {err[:n].max():.1e}, conductor {err[n:2 * n][keep[n:2 * n]].max():.1e}, "
           f"dielectric {err[2 * n:][keep[2 * n:]].max():.1e}")
     assert np.array_equal(o[keep, 3] > 0.5, valid[keep])
-    assert err[keep].max() < 5e-6
+    assert err[keep].max() < 2e-6  # measured 4e-7
