@@ -198,7 +198,12 @@ int prt_generate_rays(prt_ctx* ctx, uint64_t seed, uint32_t s0, uint32_t s1, int
 
 /* closest hit.  Replaces Scene.hit/hit_faster core/scene.py:59-73,
  * BVH.hit accelerators/bvh.py:218-237, World.hit_all
- * mathematics/intersection_taichi.py:238-291. */
+ * mathematics/intersection_taichi.py:238-291.
+ * Accept rule = the reference's numba kernel (mathematics/intersection.py:42-65): tmin <= t <= bound,
+ * u >= 0, v >= 0, u + v <= 1, all inclusive, no back-face culling; closest = min t, lowest global id on
+ * exact ties (:106-116, core/scene.py:66-73).  The strict f32 rule of the Taichi draft
+ * (mathematics/intersection_taichi.py:69-91: t0 < t < t1, 0 <= u <= 1) is NOT offered: the numba code is
+ * the only intersection code of the reference that runs, and the oracle is pinned to it. */
 int prt_trace_closest(prt_ctx* ctx, const prt_ray* rays_dev, uint64_t n, prt_hit* hits_dev,
                       uint32_t flags, void* stream);
 /* any hit in [tmin,tmax] (shadow rays, core/tracing.py:101-102): occluded_dev[i] = 0/1 */

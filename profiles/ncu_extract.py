@@ -1,6 +1,6 @@
 """ncu report -> small JSON of the counters bench.py and DESIGN.md quote (run on the CPU box).
 
-  python profiles/ncu_extract.py gpurun_out/prof.ncu-rep profiles/ncu_<name>.json [kernel-substring] [note]
+  python profiles/ncu_extract.py gpurun_out/prof.ncu-rep profiles/ncu_<name>.json [kernel-substring] [note] [key=number ...]
 
 Writes, per captured launch of the first kernel whose name contains the substring: duration, DRAM bytes
 (read + write = roofline.traffic), L1 data-pipe / L2 / issue utilisation, SIMT lanes per instruction,
@@ -70,6 +70,9 @@ def main():
     rec["source_fingerprint"] = fingerprint()
     rec["report"] = os.path.basename(rep)
     rec["note"] = note
+    for kv in sys.argv[5:]:
+        k, v = kv.split("=", 1)
+        rec[k] = float(v)
     json.dump(rec, open(out, "w"), indent=1, sort_keys=True)
     print(json.dumps(rec, indent=1, sort_keys=True))
 

@@ -28,16 +28,16 @@ constexpr int kPStack = 16;     // levels kept in shared memory; deeper ones in 
 constexpr int kPStackOvf = kMaxStack + 1;  // local-memory spill area: [0].x = spilled count, entries from [1]
 constexpr uint32_t kDone = kNoChild;  // has kLeafFlag set
 
+// |d| < 1e-20 -> +-1e-20 with the sign that `d < 0` sees: -0.0 counts as positive, like the octant
+// flags below (copysign would give -1e-20, a reciprocal of -1e20 under a "positive" octant: near and
+// far planes swapped, and a ray travelling inside a slab would miss every box)
 __device__ __forceinline__ float clamp_dir(float d) {
-    return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
+    return fabsf(d) < 1e-20f ? (d < 0.0f ? -1e-20f : 1e-20f) : d;
 }
 
 struct RayBox {  // per-ray constants of the slab test
     float3 o, idir;
-    // octant, from the sign of idir (clamp_dir keeps the sign, also of -0.0: a flag taken from
-    // `d < 0` would call -0.0 positive while its reciprocal is -1e20, and swap near and far)
-    bool negx, negy, negz;
-    __device__ __forceinline__ void set_octant() { negx = idir.x < 0.0f; negy = idir.y < 0.0f; negz = idir.z < 0.0f; }
+    bool negx, negy, negz;  // octant (consistent with clamp_dir: d < 0)
 };
 
 __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
@@ -45,7 +45,7 @@ __device__ __forceinline__ RayBox make_raybox(float3 o, float3 d) {
     r.o = o;
     r.idir = make_float3(__fdiv_rn(1.0f, clamp_dir(d.x)), __fdiv_rn(1.0f, clamp_dir(d.y)),
                          __fdiv_rn(1.0f, clamp_dir(d.z)));
-    r.set_octant();
+    r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
     return r;
 }
 
@@ -53,7 +53,7 @@ __device__ __forceinline__ RayBox make_raybox_fast(float3 o, float3 d) {  // per
     RayBox r;
     r.o = o;
     r.idir = make_float3(rcp_fast(clamp_dir(d.x)), rcp_fast(clamp_dir(d.y)), rcp_fast(clamp_dir(d.z)));
-    r.set_octant();
+    r.negx = d.x < 0.0f; r.negy = d.y < 0.0f; r.negz = d.z < 0.0f;
     return r;
 }
 

@@ -84,13 +84,15 @@ def main(scene_file=DEFAULT_SCENE, samples=8, max_depth=5, width=None, height=No
 
 
 def main_progressive(scene_file=DEFAULT_SCENE, iterations=1001, max_depth=16, seed=1, out="out.png",
-                     interval=10, save_every=100, device=0):
+                     interval=10, save_every=100, device=0, width=None, height=None):
     """Progressive driver in the shape of the reference's Taichi loop (main_taichi.py:102-127):
     one sample per pixel per iteration into the same accumulation buffer, a "samples/s" line
     every `interval` iterations, sqrt-tonemapped image every `save_every`, stop after `iterations`.
     Exactly resumable: iteration k is Philox sample index k."""
     import torch
     a_scene, a_camera = read_file(scene_file)
+    if width and height:
+        a_camera.resolution = [width, height]
     accum = tracing.new_accum(a_camera, device)
     last_t = time.time()
     for iteration in range(iterations):

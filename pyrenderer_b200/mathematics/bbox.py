@@ -2,7 +2,8 @@
 
 Only the bookkeeping half of reference mathematics/bbox.py:29-74 lives here;
 the ray/box slab test (bbox.py:6-26) is device code
-(csrc/intersect.cuh::slab_test) because nothing on the host traverses boxes.
+(csrc/bvh.cuh::node_test4, four quantised child boxes per visit) because nothing on the host
+traverses boxes.
 """
 import numpy as np
 
