@@ -832,6 +832,9 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
         if (stats) *stats = st;
         return PRT_OK;
     }
+    // the build overwrites the context's node / triangle buffers in place: nothing launched earlier (on
+    // any stream, including non-blocking ones the default stream does not wait for) may still traverse them
+    BUILD_TRY(cudaDeviceSynchronize());
     cudaEvent_t* ev = ctx->build_ev;
     for (int k = 0; k < 7; ++k)
         if (!ev[k]) BUILD_TRY(cudaEventCreate(&ev[k]));

@@ -314,3 +314,33 @@ def test_thin_lens_camera_host_and_oracle(cornell):
     assert np.abs(o[:, 2]).max() < 1e-6 and np.abs(o[:, :2]).max() <= 0.2 + 1e-6 and o[:, :2].std(axis=0).min() > 0.08
     rays0 = oracle.generate_rays(oc_pin, seed=4, s0=0, s1=8, jitter=True)
     assert np.all(rays0[..., 0:3] == np.array([0.0, 1.0, 6.8], np.float32))
+
+
+def test_ncu_profiles_carry_a_source_fingerprint_and_bench_refuses_stale_ones(tmp_path, monkeypatch, capsys):
+    """profiles/ncu_*.json hold hardware counters captured under ncu; each is stamped with the fingerprint
+    of the CUDA sources it belongs to.  bench.py quotes a counter only while the fingerprint matches and
+    says so loudly (stderr + "stale") when it does not."""
+    import glob
+    import json
+    import bench
+    from pyrenderer_b200.kernel_fingerprint import fingerprint
+    fp = fingerprint()
+    assert len(fp) == 16 and fp == fingerprint()
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_*.json")))
+    assert files, "no committed ncu profile"
+    for f in files:
+        rec = json.load(open(f))
+        for key in ("kernel", "duration_ns", "dram_bytes", "source_fingerprint", "l1_data_pipe_pct", "lanes_per_instruction"):
+            assert key in rec, (f, key)
+        assert rec["duration_ns"] > 0 and rec["dram_bytes"] > 0
+    name = os.path.basename(files[0])[4:-5]
+    rec = bench.ncu_profile(name)
+    assert rec is not None and (rec.get("stale") or rec["source_fingerprint"] == fp)
+    # a profile captured from other sources is refused, loudly
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    os.makedirs(tmp_path / "profiles")
+    json.dump({"source_fingerprint": "0" * 16, "dram_bytes": 1.0}, open(tmp_path / "profiles" / "ncu_x.json", "w"))
+    out = bench.ncu_profile("x")
+    assert out["stale"] is True and "dram_bytes" not in out
+    assert "STALE" in capsys.readouterr().err
+    assert bench.ncu_profile("missing") is None
