@@ -9,12 +9,8 @@ VDIR = os.path.join(ROOT, "pyrenderer_b200", "variants")
 # -6 %, PRMT+FADD byte->float instead of I2F.U8 -8 %, L1 prefetch of the far child 0 %, smem stack
 # depth 8/12/16 no effect -- none of them is in the tree any more; add -D switches here to try new ones.
 VARIANTS = {
-    "cur": (),
-    "nosent": ("-DPRT_SENTINEL=0",),
-    "nocomp": ("-DPRT_COMPACT_RAY=0",),
-    "nosent_nocomp": ("-DPRT_SENTINEL=0", "-DPRT_COMPACT_RAY=0"),
-    "x7": ("-DPRT_MIN_BLOCKS_EXACT=7",),
-    "x7_nosent_nocomp": ("-DPRT_MIN_BLOCKS_EXACT=7", "-DPRT_SENTINEL=0", "-DPRT_COMPACT_RAY=0"),
+    "base": (),
+    "smin": ("-DPRT_STACK_MIN=1",),
 }
 if sys.argv[1] == "build":
     from pyrenderer_b200 import build
