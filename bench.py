@@ -570,6 +570,8 @@ def soup_leg(args, ctx, torch, _abi, dev, rank, world, local, n_tris, barrier, m
     out = {"workload": f"soup-{n_tris} closest-hit: {RAYS_PER_BATCH} incoherent rays per step per GPU (origins U[0,1]^3, directions uniform "
                        "on S^2), BVH replicated, no collective (weak)",
            "l2": "inputs larger than L2: 512 MiB of rays + 256 MiB of hits per step, 4 rotating batches",
+           "ray_binning": ("on by default: BVH of %.0f MB > 96 MB (rays counting-sorted by origin cell before the traversal, inside the timed step)"
+                           if st["n_nodes"] * 64 + n_tris * 40 > (96 << 20) else "off by default: BVH of %.0f MB lives in L2") % ((st["n_nodes"] * 64 + n_tris * 40) / 2**20),
            "bvh": st, "bvh_build_ms_median": float(np.median(build_ms)), "bvh_build_wall_ms_median": float(np.median(build_wall)),
            "bvh_build_mtris_per_s": n_tris / np.median(build_wall) / 1e3, "steps": steps}
     modes = {}
@@ -602,7 +604,7 @@ def soup_leg(args, ctx, torch, _abi, dev, rank, world, local, n_tris, barrier, m
                 "achieved": achieved, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "frac_meaning": "SURVEY 8(d) nominal: algorithmic bytes / kernel time / HBM peak (the BVH may be L2-resident: see dram_frac)",
                 "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri, "kernel_ms": kern_ms,
-                "fixup_ms": prof["exact_fixup"][0] / steps, "traffic": None, "bound": "see ncu profile (not captured)", "ncu": ncu}
+                "fixup_ms": prof["exact_fixup"][0] / steps, "binning_ms": prof["other"][0] / steps, "traffic": None, "bound": "see ncu profile (not captured)", "ncu": ncu}
         if ncu and not ncu.get("stale"):
             roof["traffic"] = ncu["dram_bytes"]
             roof["dram_frac"] = ncu["dram_bytes"] / (ncu["duration_ns"] * 1e-9) / 1e9 / hbm_peak

@@ -23,7 +23,7 @@ BSDF_QUERY_DTYPE = np.dtype([("d", "<f4", 3), ("type", "<u4"), ("ns", "<f4", 3),
 assert BSDF_QUERY_DTYPE.itemsize == 64
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("tri", "<i4")])
 
-TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE = 1, 2, 4
+TRACE_EXACT, TRACE_COUNT, TRACE_BRUTE, TRACE_BIN, TRACE_NO_BIN = 1, 2, 4, 8, 16
 RENDER_EXACT_PRIMARY = 1
 RENDER_PHYSICAL = 2
 RENDER_COUNT = 4

@@ -974,6 +974,10 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
     st.n_nodes = n_rec;
     st.sah_cost = (n > 1 && root_hi.w > 0.f) ? root_lo.w / root_hi.w : 0.f;
+    if (n > 1) {
+        ctx->scene_lo[0] = root_lo.x; ctx->scene_lo[1] = root_lo.y; ctx->scene_lo[2] = root_lo.z;
+        ctx->scene_hi[0] = root_hi.x; ctx->scene_hi[1] = root_hi.y; ctx->scene_hi[2] = root_hi.z;
+    }
     st.ms_morton = ms[0]; st.ms_sort = ms[1]; st.ms_hierarchy = ms[2]; st.ms_refit = ms[3];
     st.ms_emit = ms[5];
     st.ms_total = ms[0] + ms[1] + ms[2] + ms[3] + ms[4] + ms[5];

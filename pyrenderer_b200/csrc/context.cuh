@@ -41,6 +41,11 @@ struct prt_ctx {
     prt_camera cam = {};
     bool cam_set = false;
 
+    // ray binning (traverse.cu): scene box from the last build, per-slot sort scratch (keys x2, vals x2, radix temp)
+    float scene_lo[3] = {0.f, 0.f, 0.f}, scene_hi[3] = {1.f, 1.f, 1.f};
+    void* bin_scratch[4] = {};
+    size_t bin_scratch_bytes[4] = {};
+
     // counters + exact-mode scratch: one (flag list, flag count) pair per in-flight EXACT launch,
     // so that the host-buffer pipeline can keep two exact traces on two streams
     prt::Counters* counters = nullptr;  // device

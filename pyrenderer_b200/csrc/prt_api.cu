@@ -212,6 +212,7 @@ void prt_destroy(prt_ctx* ctx) {
     for (auto& e : ctx->prof_events) cudaEventDestroy(e);
     for (auto& e : ctx->build_ev) if (e) cudaEventDestroy(e);
     for (auto& l : ctx->flag_list) cudaFree(l);
+    for (auto& b : ctx->bin_scratch) cudaFree(b);
     cudaFree(ctx->counters); cudaFree(ctx->flag_count);
     cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]); cudaFree(ctx->fetch_counters);
     for (auto& s : ctx->copy_stream) if (s) cudaStreamDestroy(s);
@@ -456,6 +457,7 @@ int prt_release_scratch(prt_ctx* ctx) {
     cudaFree(ctx->shard_accum);
     ctx->shard_accum = nullptr; ctx->shard_bytes = 0;
     for (unsigned k = 0; k < prt_ctx::kFlagRing; ++k) { cudaFree(ctx->flag_list[k]); ctx->flag_list[k] = nullptr; ctx->flag_cap[k] = 0; }
+    for (int k = 0; k < 4; ++k) { cudaFree(ctx->bin_scratch[k]); ctx->bin_scratch[k] = nullptr; ctx->bin_scratch_bytes[k] = 0; }
     wavefront_free(ctx);
     return PRT_OK;
 }

@@ -24,7 +24,7 @@ inline size_t radix_sort_temp_bytes(uint32_t n) {
     return sizeof(uint32_t) * (256 * (tiles ? tiles : 1) + 256 + 256 + 1);
 }
 
-__global__ void __launch_bounds__(kRsThreads)
+static __global__ void __launch_bounds__(kRsThreads)
 rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t ntiles, uint32_t* hist) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
@@ -41,7 +41,7 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_
 
 // block d scans row d (length ntiles) in place; totals[d] = row sum.  The last block to
 // arrive turns totals into exclusive digit bases.
-__global__ void __launch_bounds__(kRsThreads)
+static __global__ void __launch_bounds__(kRsThreads)
 rs_scan_kernel(uint32_t* hist, uint32_t ntiles, uint32_t* totals, uint32_t* bases, uint32_t* arrive) {
     __shared__ uint32_t warp_sum[kRsThreads / 32];
     __shared__ uint32_t carry;
@@ -90,7 +90,7 @@ rs_scan_kernel(uint32_t* hist, uint32_t ntiles, uint32_t* totals, uint32_t* base
     }
 }
 
-__global__ void __launch_bounds__(kRsThreads)
+static __global__ void __launch_bounds__(kRsThreads)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   uint32_t* keys_out, uint32_t* vals_out, uint32_t n, int shift, uint32_t ntiles,
                   const uint32_t* __restrict__ hist, const uint32_t* __restrict__ bases) {

@@ -72,14 +72,84 @@ trace_kernel(SceneDev sc, const float4* __restrict__ rays, uint64_t n, void* out
 }
 
 // Throughput path (plain FP32, BVH): persistent warps with dynamic ray fetch (persist.cuh).
+// Ray binning (PRT_TRACE_BIN): 8-bit key = cell of the ray origin in an 8 x 8 x 4 grid over the scene box
+// (origins outside are clamped onto it), and ONE counting-sort pass over ray indices gives the order in which
+// the persistent warps fetch the rays.  Three launches over tiles of 4096 rays:
+//   bin_count_kernel    key per ray (stored as a byte), per-tile histogram in shared memory -> global bin counts
+//   bin_scan_kernel     exclusive scan of the 256 counts -> bin cursors
+//   bin_scatter_kernel  rank inside the tile by shared-memory atomics, one global reservation per bin per tile
+// The order inside a bin is whatever the atomics give (it only changes which warp traces which ray).
+constexpr int kBinTile = 4096, kBinThreads = 256;
+__global__ void __launch_bounds__(kBinThreads)
+bin_count_kernel(const float4* __restrict__ rays, unsigned int n, float3 lo, float3 scale, uint8_t* keys, unsigned int* hist) {
+    __shared__ unsigned int cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned int base = blockIdx.x * kBinTile;
+#pragma unroll 4
+    for (int r = 0; r < kBinTile / kBinThreads; ++r) {
+        const unsigned int i = base + r * kBinThreads + threadIdx.x;
+        if (i < n) {
+            const float4 o = __ldg(rays + 2ull * i);
+            const int x = min(max((int)((o.x - lo.x) * scale.x), 0), 7), y = min(max((int)((o.y - lo.y) * scale.y), 0), 7),
+                      z = min(max((int)((o.z - lo.z) * scale.z), 0), 3);
+            const unsigned int k = (unsigned int)((z << 6) | (y << 3) | x);
+            keys[i] = (uint8_t)k;
+            atomicAdd(&cnt[k], 1u);
+        }
+    }
+    __syncthreads();
+    if (cnt[threadIdx.x]) atomicAdd(&hist[threadIdx.x], cnt[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) bin_scan_kernel(unsigned int* hist_to_cursor) {
+    __shared__ unsigned int s[256];
+    const unsigned int v = hist_to_cursor[threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const unsigned int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    hist_to_cursor[threadIdx.x] = s[threadIdx.x] - v;
+}
+__global__ void __launch_bounds__(kBinThreads)
+bin_scatter_kernel(const uint8_t* __restrict__ keys, unsigned int n, unsigned int* cursor, uint32_t* perm) {
+    __shared__ unsigned int cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned int base = blockIdx.x * kBinTile;
+    unsigned int key[kBinTile / kBinThreads], rank[kBinTile / kBinThreads];
+#pragma unroll
+    for (int r = 0; r < kBinTile / kBinThreads; ++r) {
+        const unsigned int i = base + r * kBinThreads + threadIdx.x;
+        key[r] = 256u;
+        if (i < n) {
+            key[r] = keys[i];
+            rank[r] = atomicAdd(&cnt[key[r]], 1u);
+        }
+    }
+    __syncthreads();
+    const unsigned int c = cnt[threadIdx.x];
+    __syncthreads();
+    cnt[threadIdx.x] = c ? atomicAdd(&cursor[threadIdx.x], c) : 0u;  // this tile's range of the bin
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kBinTile / kBinThreads; ++r)
+        if (key[r] < 256u) perm[cnt[key[r]] + rank[r]] = base + r * kBinThreads + threadIdx.x;
+}
+
 template <int MODE>
 struct ApiIO {
     const float4* rays;
     void* out;
+    const uint32_t* perm;      // ray order of this launch (binning), or nullptr = as given
     uint32_t* flag_list;       // EXACT only
     unsigned int* flag_count;
     bool aligned32;  // ray array on a 32-byte boundary (any cudaMalloc'd / torch buffer): one 256-bit load per ray
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
+        if (perm) k = __ldcs(perm + k);
         // rays and hits stream through once: evict-first, so they do not push the BVH out of L2
         if (aligned32) {
             ldg256_cs(rays + 2ull * k, ro, rd);
@@ -113,10 +183,10 @@ struct ApiIO {
 #endif
 template <int MODE, bool COUNT, bool EXACT>
 __global__ void __launch_bounds__(kTraceThreads, EXACT ? PRT_MIN_BLOCKS_EXACT : PRT_MIN_BLOCKS)
-trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out,
+trace_persistent_kernel(SceneDev sc, const float4* __restrict__ rays, unsigned int n, void* out, const uint32_t* perm,
                         unsigned int* fetch, uint32_t* flag_list, unsigned int* flag_count, Counters* ctr) {
     __shared__ uint2 s_stack[kPStack][kTraceThreads];
-    ApiIO<MODE> io{rays, out, flag_list, flag_count, (reinterpret_cast<uintptr_t>(rays) & 31u) == 0u};
+    ApiIO<MODE> io{rays, out, perm, flag_list, flag_count, (reinterpret_cast<uintptr_t>(rays) & 31u) == 0u};
     trace_persistent<MODE, COUNT, EXACT>(sc, io, fetch, n, &s_stack[0][threadIdx.x], ctr);
 }
 
@@ -232,9 +302,38 @@ int launch_trace(prt_ctx* ctx, int mode, const float4* rays, uint64_t n, void* o
         unsigned g = (unsigned)(exact ? ctx->grid_persist_exact : ctx->grid_persist);
         unsigned need = (unsigned)((n + kTraceThreads - 1) / kTraceThreads);
         if (need < g) g = need;
+        // ray binning: explicit, or by default when the BVH cannot live in L2 and the batch is large
+        const size_t bvh_bytes = (size_t)ctx->n_nodes * sizeof(Node64) + (size_t)ctx->nt * 40u;
+        const bool bin = !(flags & PRT_TRACE_NO_BIN) && ((flags & PRT_TRACE_BIN) || (bvh_bytes > (96u << 20) && n >= (1u << 20)));
+        const uint32_t* perm = nullptr;
+        if (bin) {
+            const unsigned slot = flag_slot % 4u;
+            const size_t nz = ((size_t)n + 255) & ~(size_t)255, need = 5 * nz + 1024;  // perm (u32), keys (u8), 256 cursors
+            if (ctx->bin_scratch_bytes[slot] < need) {
+                PRT_CUDA_TRY(ctx, cudaDeviceSynchronize());
+                cudaFree(ctx->bin_scratch[slot]);
+                ctx->bin_scratch[slot] = nullptr; ctx->bin_scratch_bytes[slot] = 0;
+                PRT_CUDA_TRY(ctx, cudaMalloc(&ctx->bin_scratch[slot], need));
+                ctx->bin_scratch_bytes[slot] = need;
+            }
+            uint32_t* perm_buf = (uint32_t*)ctx->bin_scratch[slot];
+            uint8_t* keys = (uint8_t*)(perm_buf + nz);
+            unsigned int* cursor = (unsigned int*)(keys + nz);
+            const float3 lo = make_float3(ctx->scene_lo[0], ctx->scene_lo[1], ctx->scene_lo[2]);
+            const float ex = ctx->scene_hi[0] - lo.x, ey = ctx->scene_hi[1] - lo.y, ez = ctx->scene_hi[2] - lo.z;
+            const float3 scale = make_float3(ex > 0.f ? 8.0f / ex : 0.f, ey > 0.f ? 8.0f / ey : 0.f, ez > 0.f ? 4.0f / ez : 0.f);
+            const unsigned tiles = (unsigned)((n + kBinTile - 1) / kBinTile);
+            PRT_CUDA_TRY(ctx, cudaMemsetAsync(cursor, 0, 256 * sizeof(unsigned int), stream));
+            prof_begin(ctx, PROF_OTHER, stream, 3);
+            bin_count_kernel<<<tiles, kBinThreads, 0, stream>>>(rays, (unsigned)n, lo, scale, keys, cursor);
+            bin_scan_kernel<<<1, 256, 0, stream>>>(cursor);
+            bin_scatter_kernel<<<tiles, kBinThreads, 0, stream>>>(keys, (unsigned)n, cursor, perm_buf);
+            prof_end(ctx, stream);
+            perm = perm_buf;
+        }
         prof_begin(ctx, mode == MODE_CLOSEST ? PROF_CLOSEST : PROF_SHADOW, stream);
 #define PRT_PERSIST(M, C, E) trace_persistent_kernel<M, C, E><<<g, kTraceThreads, 0, stream>>>( \
-        sc, rays, (unsigned)n, out0, fetch, flag_list, flag_count, ctx->counters)
+        sc, rays, (unsigned)n, out0, perm, fetch, flag_list, flag_count, ctx->counters)
         if (mode == MODE_CLOSEST) {
             if (exact) { if (count) PRT_PERSIST(MODE_CLOSEST, true, true); else PRT_PERSIST(MODE_CLOSEST, false, true); }
             else { if (count) PRT_PERSIST(MODE_CLOSEST, true, false); else PRT_PERSIST(MODE_CLOSEST, false, false); }

@@ -567,7 +567,7 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
             if (b == 0 && (p->flags & PRT_RENDER_EXACT_PRIMARY)) {
                 // bounce 0: queue == identity, rays contiguous -> the API-level exact trace applies
                 rc = launch_trace(ctx, MODE_CLOSEST, w->rays, n_paths, w->hits, nullptr,
-                                  PRT_TRACE_EXACT | (counted ? PRT_TRACE_COUNT : 0u), stream);
+                                  PRT_TRACE_EXACT | PRT_TRACE_NO_BIN | (counted ? PRT_TRACE_COUNT : 0u), stream);  // (camera rays: already in pixel order)
                 if (rc != PRT_OK) return rc;
             } else {
                 prof_begin(ctx, PROF_CLOSEST, stream);

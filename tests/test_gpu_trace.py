@@ -506,3 +506,38 @@ def test_morton_63_bit_keys_and_grow_only_buffers(gpu_ctx):
     assert np.array_equal(ids2, ids63)
     st2 = gpu_ctx.build_bvh()
     assert st2["n_tris"] == 50000
+
+
+def test_ray_binning_changes_the_order_not_the_answers(gpu_ctx):
+    """PRT_TRACE_BIN: rays are counting-sorted by the cell of their origin before the traversal (indices
+    only).  Every mode must return, bit for bit, what it returns without binning -- also for origins
+    outside the scene box, a ragged batch, and the chunked host pipeline."""
+    from pyrenderer_b200 import _abi
+    torch = _torch()
+    tris = random_soup(30000, seed=91)
+    n = 300001
+    rays = random_rays(n, seed=92)
+    rays[:1000, 0:3] = rays[:1000, 0:3] * 8.0 - 3.0  # origins far outside the unit box
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build_bvh()
+    r = torch.from_numpy(rays).cuda()
+    for flags in (0, EXACT):
+        h0 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+        h1 = torch.full((n, 4), -7.0, dtype=torch.float32, device="cuda")
+        gpu_ctx.trace_closest(r, n, h0, flags | _abi.TRACE_NO_BIN)
+        gpu_ctx.trace_closest(r, n, h1, flags | _abi.TRACE_BIN)
+        torch.cuda.synchronize()
+        assert torch.equal(h0.view(torch.int32), h1.view(torch.int32)), flags
+    o0 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    o1 = torch.full((n,), 9, dtype=torch.uint8, device="cuda")
+    rs = rays.copy(); rs[:, 7] = 0.3
+    rsd = torch.from_numpy(rs).cuda()
+    gpu_ctx.trace_any(rsd, n, o0, _abi.TRACE_NO_BIN)
+    gpu_ctx.trace_any(rsd, n, o1, _abi.TRACE_BIN)
+    torch.cuda.synchronize()
+    assert torch.equal(o0, o1) and 0.05 < o0.float().mean().item() < 0.99
+    ids_o = oracle.closest_hit(tris, rays[:3000])[0]
+    hb = gpu_ctx.trace_closest_host(rays, EXACT | _abi.TRACE_BIN)
+    assert np.array_equal(hb["tri"][:3000], ids_o)
+    hn = gpu_ctx.trace_closest_host(rays, EXACT | _abi.TRACE_NO_BIN)
+    assert np.array_equal(hb.view(np.uint32), hn.view(np.uint32))
