@@ -224,6 +224,18 @@ __global__ void hierarchy_kernel(const uint32_t* __restrict__ keys_lo, const uin
     range[i] = make_int2(min(i, j), max(i, j));  // sorted positions covered by node i (contiguous)
 }
 
+__device__ __forceinline__ float box_area(float3 lo, float3 hi) {
+    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return 2.0f * (ex * ey + ey * ez + ez * ex);
+}
+
+struct RefitParams {
+    int n;
+    uint32_t max_leaf;
+    float cn, ct;
+    int rotations;
+};
+
 // ---- SAH treelets -------------------------------------------------------------------------
 // The Morton hierarchy is a spatial-median tree: fine at the top, but inside a neighbourhood of a
 // few dozen triangles a surface-area-heuristic builder separates them better.  Every MAXIMAL
@@ -237,6 +249,11 @@ __global__ void hierarchy_kernel(const uint32_t* __restrict__ keys_lo, const uin
 #endif
 constexpr int kTreelet = PRT_TREELET;  // <= 255 (8-bit permutation)
 constexpr int kTreeletWarps = 4;  // warps per block
+#ifndef PRT_TREELET_FINE
+#define PRT_TREELET_FINE 32  // one-chunk ranges with more triangles than this use 16 bins instead of 8
+#endif
+constexpr int kTreeletStack = 16;  // the larger child is pushed first, so the stack holds <= log2(kTreelet) + 1 ranges
+constexpr int kTreeletWords = (kTreelet + 31) / 32;
 
 __global__ void treelet_roots_kernel(const int2* __restrict__ range, const int* __restrict__ parent, int n,
                                      int* roots, unsigned int* n_roots) {
@@ -258,7 +275,8 @@ struct TreeletShared {
     uint8_t order[kTreelet], tmp[kTreelet];   // permutation being partitioned
     uint32_t pk[kTreelet];                    // per position of the current range: bin per axis, 8 bits each
     int names[kTreelet];                      // internal node names available to this subtree; [0] = root
-    int stack[kTreelet][3];                   // begin, end, name
+    uint32_t link[kTreelet];                  // per names index: children, 16 bits each (0x8000 | position = leaf, else names index)
+    int stack[kTreeletStack][3];              // begin, end, names index
     int bins[3][16][8];                       // per (axis, bin): ordered-int box lo.xyz, hi.xyz, count, pad
 };
 
@@ -272,45 +290,63 @@ __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
 // scans inside an NB-lane group; candidate plane j = "bins <= j go left".  NB = 16: two rounds
 // (axes x,y then z); NB = 8: the 24 (axis, bin) pairs fit one round.  Returns cost (inf: none).
 template <int NB>
-__device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int e, const float cmin[3],
-                                                    const float scale[3], int lane, int& best_slot) {
-    const unsigned FULL = 0xffffffffu;
-    const float inf = __int_as_float(0x7f800000);
-    constexpr int kAxesPerRound = 32 / NB;             // 2 or 4 (4th group idle)
-    constexpr int kRounds = NB == 16 ? 2 : 1;
-    float best = inf;
-    best_slot = -1;
-    // Bin boxes by shared-memory atomics on order-preserving ints (min / max do not depend on the order
-    // of arrival, so the result is the same as a scan): one triangle per lane and step.  (Round 1 had
-    // every (axis, bin) lane scan the whole range for its members -- 32 x c loop trips for c useful
-    // ones, the bulk of the 0.9 ms the treelets took at 1M triangles.)
+__device__ __forceinline__ void treelet_bins_clear(TreeletShared& S, int lane) {
     for (int k = lane; k < 3 * NB; k += 32) {
         int* bb = S.bins[k / NB][k % NB];
         bb[0] = bb[1] = bb[2] = 0x7fffffff;              // f2ord(+inf) <= this
         bb[3] = bb[4] = bb[5] = (int)0x80000000;
         bb[6] = 0;
     }
+}
+// one triangle into its bin of every axis; returns the three bin indices, 8 bits each
+template <int NB>
+__device__ __forceinline__ uint32_t treelet_bin_add(TreeletShared& S, const float lo[3], const float hi[3],
+                                                    const float cmin[3], const float scale[3]) {
+    const int l0 = f2ord(lo[0]), l1 = f2ord(lo[1]), l2 = f2ord(lo[2]);
+    const int h0 = f2ord(hi[0]), h1 = f2ord(hi[1]), h2 = f2ord(hi[2]);
+    uint32_t pk = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int j = (int)((0.5f * (lo[a] + hi[a]) - cmin[a]) * scale[a]);
+        j = j > NB - 1 ? NB - 1 : j;
+        pk |= (uint32_t)j << (8 * a);
+        if (scale[a] > 0.0f) {
+            int* bb = S.bins[a][j];
+            atomicMin(bb + 0, l0); atomicMin(bb + 1, l1); atomicMin(bb + 2, l2);
+            atomicMax(bb + 3, h0); atomicMax(bb + 4, h1); atomicMax(bb + 5, h2);
+            atomicAdd(bb + 6, 1);
+        }
+    }
+    return pk;
+}
+template <int NB>
+__device__ __forceinline__ float treelet_pick(TreeletShared& S, const float scale[3], int lane, int& best_slot);
+
+template <int NB>
+__device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int e, const float cmin[3],
+                                                    const float scale[3], int lane, int& best_slot) {
+    // Bin boxes by shared-memory atomics on order-preserving ints (min / max do not depend on the order
+    // of arrival, so the result is the same as a scan): one triangle per lane and step.  (Round 1 had
+    // every (axis, bin) lane scan the whole range for its members -- 32 x c loop trips for c useful
+    // ones, the bulk of the 0.9 ms the treelets took at 1M triangles.)
+    treelet_bins_clear<NB>(S, lane);
     __syncwarp();
     for (int k = b + lane; k < e; k += 32) {
         const int q = S.order[k];
-        uint32_t pk = 0;
-        const int l0 = f2ord(S.lo[q][0]), l1 = f2ord(S.lo[q][1]), l2 = f2ord(S.lo[q][2]);
-        const int h0 = f2ord(S.hi[q][0]), h1 = f2ord(S.hi[q][1]), h2 = f2ord(S.hi[q][2]);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            int j = (int)((0.5f * (S.lo[q][a] + S.hi[q][a]) - cmin[a]) * scale[a]);
-            j = j > NB - 1 ? NB - 1 : j;
-            pk |= (uint32_t)j << (8 * a);
-            if (scale[a] > 0.0f) {
-                int* bb = S.bins[a][j];
-                atomicMin(bb + 0, l0); atomicMin(bb + 1, l1); atomicMin(bb + 2, l2);
-                atomicMax(bb + 3, h0); atomicMax(bb + 4, h1); atomicMax(bb + 5, h2);
-                atomicAdd(bb + 6, 1);
-            }
-        }
-        S.pk[k] = pk;
+        S.pk[k] = treelet_bin_add<NB>(S, S.lo[q], S.hi[q], cmin, scale);
     }
     __syncwarp();
+    return treelet_pick<NB>(S, scale, lane, best_slot);
+}
+
+template <int NB>
+__device__ __forceinline__ float treelet_pick(TreeletShared& S, const float scale[3], int lane, int& best_slot) {
+    const unsigned FULL = 0xffffffffu;
+    const float inf = __int_as_float(0x7f800000);
+    constexpr int kAxesPerRound = 32 / NB;             // 2 or 4 (4th group idle)
+    constexpr int kRounds = NB == 16 ? 2 : 1;
+    float best = inf;
+    best_slot = -1;
 #pragma unroll
     for (int round = 0; round < kRounds; ++round) {
         const int a = lane / NB + kAxesPerRound * round, bin = lane % NB;
@@ -359,10 +395,24 @@ __device__ __forceinline__ float treelet_best_split(TreeletShared& S, int b, int
     return __uint_as_float(kmin);
 }
 
+// FUSED: the warp that built a subtree also refits it -- boxes, SAH cost, leaf collapse, triangle and
+// record counts of every node of the subtree, exactly what refit_kernel derives bottom-up (update_node), and
+// marks the subtree's leaves as covered (collapsed[leaf] = 2).  refit_kernel then starts at the subtree
+// ROOTS: 1 % of the leaves' arrival-flag chains are left (1M triangles: refit 0.43 -> 0.1 ms).  SAH rotations
+// are not applied inside a subtree the SAH builder has just produced.
+struct TreeletOut {
+    float4* bmin;
+    float4* bmax;
+    uint32_t* tcount;
+    uint32_t* icount;
+    uint8_t* collapsed;
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(32 * kTreeletWarps)
 treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2* __restrict__ range,
                    int* left, int* right, int* parent, int n, const int* __restrict__ roots,
-                   const unsigned int* __restrict__ n_roots) {
+                   const unsigned int* __restrict__ n_roots, TreeletOut O, RefitParams P) {
     __shared__ TreeletShared sh_all[kTreeletWarps];
     TreeletShared& S = sh_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -401,16 +451,66 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
         __syncwarp();
         // (n_names == m - 1 by construction)
         int next_name = 1, sp = 0;
-        if (lane == 0) { S.stack[0][0] = 0; S.stack[0][1] = m; S.stack[0][2] = root; }
+        if (lane == 0) { S.stack[0][0] = 0; S.stack[0][1] = m; S.stack[0][2] = 0; }
         sp = 1;
         __syncwarp();
         while (sp > 0) {
             --sp;
-            const int b = S.stack[sp][0], e = S.stack[sp][1], name = S.stack[sp][2];
+            const int b = S.stack[sp][0], e = S.stack[sp][1], ni = S.stack[sp][2];
+            const int name = S.names[ni];
             const int c = e - b;
             __syncwarp();
             int mid = b + 1;
-            if (c > 2) {
+            if (c > 2 && c <= 32) {
+                // ---- one triangle per lane: box, centroid and bins stay in registers from the centroid bounds to the
+                // partition (most splits of a subtree are of this size; same bins, same plane, same order as below)
+                const bool has = lane < c;
+                int q = 0;
+                float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+                if (has) {
+                    q = S.order[b + lane];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { lo[a] = S.lo[q][a]; hi[a] = S.hi[q][a]; }
+                }
+                float cmin[3], cmax[3], scale[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float cc = 0.5f * (lo[a] + hi[a]);  // (idle lanes: inf + -inf = NaN, replaced below)
+                    cmin[a] = ord2f(__reduce_min_sync(FULL, f2ord(has ? cc : inf)));
+                    cmax[a] = ord2f(__reduce_max_sync(FULL, f2ord(has ? cc : -inf)));
+                    scale[a] = cmax[a] > cmin[a] ? 8.0f / (cmax[a] - cmin[a]) : 0.0f;
+                }
+                uint32_t pk = 0;
+                int best_slot, nbs = 3;  // log2(bins)
+                if (c > PRT_TREELET_FINE) {
+                    nbs = 4;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) scale[a] *= 2.0f;
+                    treelet_bins_clear<16>(S, lane);
+                    __syncwarp();
+                    if (has) pk = treelet_bin_add<16>(S, lo, hi, cmin, scale);
+                    __syncwarp();
+                    treelet_pick<16>(S, scale, lane, best_slot);
+                } else {
+                    treelet_bins_clear<8>(S, lane);
+                    __syncwarp();
+                    if (has) pk = treelet_bin_add<8>(S, lo, hi, cmin, scale);
+                    __syncwarp();
+                    treelet_pick<8>(S, scale, lane, best_slot);
+                }
+                if (best_slot >= 0) {
+                    const int a = best_slot >> nbs, j = best_slot & ((1 << nbs) - 1);
+                    const bool go_left = has && (int)((pk >> (8 * a)) & 0xffu) <= j;
+                    const unsigned lm = __ballot_sync(FULL, go_left), vm = c == 32 ? FULL : (1u << c) - 1u;
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int nleft = __popc(lm);
+                    const int pos = go_left ? __popc(lm & lt) : nleft + __popc(~lm & vm & lt);
+                    if (has) S.order[b + pos] = (uint8_t)q;  // stable; every lane read its entry above
+                    mid = b + nleft;
+                } else {
+                    mid = b + c / 2;  // coincident centroids: split the range in the middle
+                }
+            } else if (c > 2) {
                 // centroid bounds
                 float cmin[3] = {inf, inf, inf}, cmax[3] = {-inf, -inf, -inf};
                 for (int k = b + lane; k < e; k += 32) {
@@ -426,14 +526,13 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                     cmin[a] = ord2f(__reduce_min_sync(FULL, f2ord(cmin[a])));
                     cmax[a] = ord2f(__reduce_max_sync(FULL, f2ord(cmax[a])));
                 }
-                // 16 bins for the large ranges near the treelet root, 8 (one round) below
-                const int nb = c > 32 ? 16 : 8;
+                // 16 bins for the large ranges near the treelet root (8, one round, in the one-chunk path above)
+                constexpr int nb = 16;
                 float scale[3];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) scale[a] = cmax[a] > cmin[a] ? (float)nb / (cmax[a] - cmin[a]) : 0.0f;
                 int best_slot;
-                if (nb == 16) treelet_best_split<16>(S, b, e, cmin, scale, lane, best_slot);
-                else treelet_best_split<8>(S, b, e, cmin, scale, lane, best_slot);
+                treelet_best_split<16>(S, b, e, cmin, scale, lane, best_slot);
                 if (best_slot >= 0) {
                     const int a = best_slot / nb, j = best_slot % nb;
                     // stable partition of order[b, e) by bin <= j
@@ -473,40 +572,119 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
             __syncwarp();
             // children: a range of one triangle is the leaf named (n-1) + its final sorted position
             const int lsize = mid - b, rsize = e - mid;
-            int lname, rname;
-            if (lsize == 1) lname = (n - 1) + first + b; else lname = S.names[next_name++];
-            if (rsize == 1) rname = (n - 1) + first + mid; else rname = S.names[next_name++];
+            const int lidx = lsize > 1 ? next_name++ : -1, ridx = rsize > 1 ? next_name++ : -1;  // names indices
             if (lane == 0) {
+                const int lname = lsize == 1 ? (n - 1) + first + b : S.names[lidx];
+                const int rname = rsize == 1 ? (n - 1) + first + mid : S.names[ridx];
                 left[name] = lname; right[name] = rname;
                 parent[lname] = name; parent[rname] = name;
-                if (lsize > 1) { S.stack[sp][0] = b; S.stack[sp][1] = mid; S.stack[sp][2] = lname; }
-                if (rsize > 1) { const int s2 = sp + (lsize > 1 ? 1 : 0); S.stack[s2][0] = mid; S.stack[s2][1] = e; S.stack[s2][2] = rname; }
+                S.link[ni] = (lsize == 1 ? 0x8000u | (uint32_t)b : (uint32_t)lidx) |
+                             ((rsize == 1 ? 0x8000u | (uint32_t)mid : (uint32_t)ridx) << 16);
+                // the larger range goes in first (the smaller one is split next): <= log2(m) + 1 entries
+                const bool l_first = lsize >= rsize;
+                int s2 = sp;
+                if (lsize > 1 && (l_first || rsize <= 1)) { S.stack[s2][0] = b; S.stack[s2][1] = mid; S.stack[s2][2] = lidx; ++s2; }
+                if (rsize > 1) { S.stack[s2][0] = mid; S.stack[s2][1] = e; S.stack[s2][2] = ridx; ++s2; }
+                if (lsize > 1 && !(l_first || rsize <= 1)) { S.stack[s2][0] = b; S.stack[s2][1] = mid; S.stack[s2][2] = lidx; }
             }
             sp += (lsize > 1 ? 1 : 0) + (rsize > 1 ? 1 : 0);
             __syncwarp();
         }
         // new order of the subtree's triangles
         for (int k = lane; k < m; k += 32) vals[first + k] = S.tri[S.order[k]];
+        if (FUSED) {
+            // leaves of the subtree (what refit_kernel writes for a leaf), marked as covered
+            for (int k = lane; k < m; k += 32) {
+                const int q = S.order[k], node = (n - 1) + first + k;
+                const float3 lo = make_float3(S.lo[q][0], S.lo[q][1], S.lo[q][2]), hi = make_float3(S.hi[q][0], S.hi[q][1], S.hi[q][2]);
+                const float sa = box_area(lo, hi);
+                __stcg(O.bmin + node, make_float4(lo.x, lo.y, lo.z, P.ct * sa));
+                __stcg(O.bmax + node, make_float4(hi.x, hi.y, hi.z, sa));
+                __stcg(O.tcount + node, 1u);
+                __stcg(O.icount + node, 0u);
+                O.collapsed[node] = 2;
+            }
+            // internal nodes bottom-up: node i (names index) is ready when both children are done; every round each
+            // lane takes one ready node of its own (i = lane + 32 j); done[j] is the ballot of the finished ones
+            // (warp-uniform registers).  Children's results come back from global memory (.cg), ordered by __syncwarp.
+            unsigned done[kTreeletWords];
+#pragma unroll
+            for (int j = 0; j < kTreeletWords; ++j) done[j] = 0u;
+            const int n_int = m - 1;
+            int n_done = 0;
+            for (int round = 0; n_done < n_int && round < 2 * kTreelet; ++round) {  // (>= 1 node per round; the cap only guards against a corrupt link)
+                __syncwarp();
+                int pick = -1;
+                uint32_t plink = 0;
+#pragma unroll
+                for (int j = 0; j < kTreeletWords; ++j) {
+                    const int i = lane + 32 * j;
+                    if (pick < 0 && i < n_int && !((done[j] >> lane) & 1u)) {
+                        const uint32_t lk = S.link[i];
+                        const uint32_t l = lk & 0xffffu, r = lk >> 16;
+                        unsigned wl = 0u, wr = 0u;
+#pragma unroll
+                        for (int jj = 0; jj < kTreeletWords; ++jj) {
+                            if ((int)((l & 0x7fffu) >> 5) == jj) wl = done[jj];
+                            if ((int)((r & 0x7fffu) >> 5) == jj) wr = done[jj];
+                        }
+                        const bool lr = (l & 0x8000u) || ((wl >> (l & 31u)) & 1u);
+                        const bool rr = (r & 0x8000u) || ((wr >> (r & 31u)) & 1u);
+                        if (lr && rr) { pick = j; plink = lk; }
+                    }
+                }
+                if (pick >= 0) {
+                    const int x = S.names[lane + 32 * pick];
+                    float4 clo[2], chi[2];
+                    uint32_t ctc[2], cic[2];
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        const uint32_t cref = s2 ? plink >> 16 : plink & 0xffffu;
+                        if (cref & 0x8000u) {
+                            const int q = S.order[cref & 0x7fffu];
+                            const float3 lo = make_float3(S.lo[q][0], S.lo[q][1], S.lo[q][2]), hi = make_float3(S.hi[q][0], S.hi[q][1], S.hi[q][2]);
+                            const float sa = box_area(lo, hi);
+                            clo[s2] = make_float4(lo.x, lo.y, lo.z, P.ct * sa);
+                            chi[s2] = make_float4(hi.x, hi.y, hi.z, sa);
+                            ctc[s2] = 1u; cic[s2] = 0u;
+                        } else {
+                            const int cn = S.names[cref];
+                            clo[s2] = __ldcg(O.bmin + cn); chi[s2] = __ldcg(O.bmax + cn);
+                            ctc[s2] = __ldcg(O.tcount + cn); cic[s2] = __ldcg(O.icount + cn);
+                        }
+                    }
+                    // (update_node, with the children in registers)
+                    const float3 lo = make_float3(fminf(clo[0].x, clo[1].x), fminf(clo[0].y, clo[1].y), fminf(clo[0].z, clo[1].z));
+                    const float3 hi = make_float3(fmaxf(chi[0].x, chi[1].x), fmaxf(chi[0].y, chi[1].y), fmaxf(chi[0].z, chi[1].z));
+                    const float sa = box_area(lo, hi);
+                    const uint32_t tc = ctc[0] + ctc[1];
+                    const float c_int = P.cn * sa + clo[0].w + clo[1].w;
+                    const float c_leaf = P.ct * (float)tc * sa;
+                    const bool col = (x != 0) && tc <= P.max_leaf && c_leaf <= c_int;
+                    __stcg(O.bmin + x, make_float4(lo.x, lo.y, lo.z, col ? c_leaf : c_int));
+                    __stcg(O.bmax + x, make_float4(hi.x, hi.y, hi.z, sa));
+                    __stcg(O.tcount + x, tc);
+                    __stcg(O.icount + x, col ? 0u : 1u + cic[0] + cic[1]);
+                    O.collapsed[x] = (uint8_t)(col ? 1 : 0);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kTreeletWords; ++j) {
+                    const unsigned nb = __ballot_sync(FULL, pick == j);
+                    done[j] |= nb;
+                    n_done += __popc(nb);
+                }
+            }
+        }
         __syncwarp();
     }
 }
 
-__device__ __forceinline__ float box_area(float3 lo, float3 hi) {
-    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
-    return 2.0f * (ex * ey + ey * ez + ez * ex);
-}
 __device__ __forceinline__ float union_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
     float3 lo = make_float3(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z));
     float3 hi = make_float3(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z));
     return box_area(lo, hi);
 }
-
-struct RefitParams {
-    int n;
-    uint32_t max_leaf;
-    float cn, ct;
-    int rotations;
-};
 
 // Everything refit_kernel reads may have been written by another SM earlier in
 // the same launch (ordered by the arrival flags), so all loads bypass L1 (.cg).
@@ -529,15 +707,19 @@ __device__ __forceinline__ void update_node(int x, const int* left, const int* r
     __stcg(collapsed + x, (uint8_t)(col ? 1 : 0));
 }
 
+// Threads [0, n): one per leaf; a leaf covered by a fused treelet (collapsed == 2) has nothing to do.
+// Threads [n, n + *n_roots) (roots != nullptr): one per fused treelet root, whose subtree is already refitted.
 __global__ void refit_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vals,
                              int* left, int* right, int* parent, float4* bmin, float4* bmax,
                              uint32_t* tcount, uint32_t* icount, uint8_t* collapsed,
-                             unsigned int* flags, RefitParams P) {
+                             unsigned int* flags, RefitParams P, const int* __restrict__ roots,
+                             const unsigned int* __restrict__ n_roots) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
     int n = P.n;
-    int node = (n - 1) + j;
-    {
+    int node;
+    if (j < n) {
+        node = (n - 1) + j;
+        if (roots && collapsed[node] == 2) return;
         float3 lo, hi;
         tri_box(verts, vals[j], lo, hi);
         float sa = box_area(lo, hi);
@@ -545,8 +727,12 @@ __global__ void refit_kernel(const float4* __restrict__ verts, const uint32_t* _
         __stcg(bmax + node, make_float4(hi.x, hi.y, hi.z, sa));
         __stcg(tcount + node, 1u);
         __stcg(icount + node, 0u);
+        if (n == 1) return;
+    } else {
+        if (!roots || (unsigned)(j - n) >= *n_roots) return;
+        node = roots[j - n];
+        if (node == 0) return;  // the whole tree is one treelet
     }
-    if (n == 1) return;
     int p = __ldcg(parent + node);
     while (true) {
         __threadfence();
@@ -907,19 +1093,31 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     if (n > 1) hierarchy_kernel<<<gN, T>>>(B.keys[sorted], keys_hi, n, B.left, B.right, B.parent, B.range);
     if (n > 2 && opt.treelets) {
         treelet_roots_kernel<<<gN, T>>>(B.range, B.parent, n, B.roots, B.n_roots);
-        treelet_sah_kernel<<<ctx->num_sms * 7, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
-                                                                   B.parent, n, B.roots, B.n_roots);
     }
-    cudaEventRecord(ev[3]);
     RefitParams P;
     P.n = n; P.max_leaf = opt.max_leaf_tris; P.cn = opt.cost_node; P.ct = opt.cost_tri;
     P.rotations = (int)opt.rotations;
+    // one refit pass: the treelet warps refit their own subtrees and refit_kernel starts at the subtree roots
+    // (repeated rotation passes re-derive everything from the leaves, so they take the unfused kernel)
+    const bool fused = n > 2 && opt.treelets && opt.rotations <= 1;
+    if (n > 2 && opt.treelets) {
+        const TreeletOut O{B.bmin, B.bmax, B.tcount, B.icount, B.collapsed};
+        if (fused)
+            treelet_sah_kernel<true><<<ctx->num_sms * 7, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
+                                                                             B.parent, n, B.roots, B.n_roots, O, P);
+        else
+            treelet_sah_kernel<false><<<ctx->num_sms * 7, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
+                                                                              B.parent, n, B.roots, B.n_roots, O, P);
+    }
+    cudaEventRecord(ev[3]);
     // rotations = k > 1 repeats the bottom-up pass: every pass re-derives boxes and costs from the
     // leaves and applies the best rotation per node again (the topology from the last pass is kept)
     for (int pass = 0; pass < (P.rotations > 1 ? P.rotations : 1); ++pass) {
         if (pass) cudaMemsetAsync(B.flags, 0, sizeof(unsigned int) * ni);
-        refit_kernel<<<gN, T>>>(ctx->verts_gid, B.vals[sorted], B.left, B.right, B.parent, B.bmin, B.bmax,
-                                B.tcount, B.icount, B.collapsed, B.flags, P);
+        // (a treelet root covers >= 3 triangles: at most n / 3 of them)
+        const unsigned g_refit = fused ? (unsigned)(((size_t)nt + nt / 3 + 1 + T - 1) / T) : gN;
+        refit_kernel<<<g_refit, T>>>(ctx->verts_gid, B.vals[sorted], B.left, B.right, B.parent, B.bmin, B.bmax,
+                                     B.tcount, B.icount, B.collapsed, B.flags, P, fused ? B.roots : nullptr, B.n_roots);
     }
     cudaEventRecord(ev[4]);
     BUILD_TRY(cudaGetLastError());
