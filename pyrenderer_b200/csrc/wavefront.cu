@@ -247,6 +247,9 @@ __device__ __forceinline__ float tri_area_gid(const SceneDev& sc, uint32_t gid) 
 #ifndef PRT_SHADE_MIN_BLOCKS
 #define PRT_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef PRT_SHADE_PREFETCH
+#define PRT_SHADE_PREFETCH 1
+#endif
 template <bool PHYS, bool LOG>
 __global__ void __launch_bounds__(256, PRT_SHADE_MIN_BLOCKS)
 shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, float4* rays,
@@ -263,13 +266,34 @@ shade_kernel(SceneDev sc, WaveParams P, uint32_t bounce, uint32_t max_depth, flo
     __shared__ unsigned int s_cnt[2][2][8], s_base[2][2];
     unsigned int parity = 0;
     // block-uniform trip count, so the barriers below are reached by every thread
+    // The path state of the NEXT block iteration is pulled into L2 while this one is shaded: the queue entry is
+    // loaded one iteration ahead and its ray / hit / throughput records are prefetched, so the dependent chain
+    // queue -> state no longer waits on DRAM twice per iteration (the kernel sat at half the issue slots and
+    // half the DRAM bandwidth, profiles/ncu_cornell_shade.json).
+    uint32_t pid_next = 0;
+#if PRT_SHADE_PREFETCH
+    if (blockIdx.x * blockDim.x + threadIdx.x < n) pid_next = queue_in[blockIdx.x * blockDim.x + threadIdx.x];
+#endif
     for (unsigned int kb = blockIdx.x * blockDim.x; kb < n; kb += stride, parity ^= 1u) {
         unsigned int k = kb + threadIdx.x;
         bool alive = false, want_shadow = false;
         uint32_t pid = 0;
         float4 sro, srd, sc4;
+#if PRT_SHADE_PREFETCH
+        const uint32_t pid_cur = pid_next;
+        if (k + stride < n) {
+            pid_next = queue_in[k + stride];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + 2 * (size_t)pid_next + 1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hits + pid_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(beta + pid_next));
+        }
+#endif
         if (k < n) {
+#if PRT_SHADE_PREFETCH
+            pid = pid_cur;
+#else
             pid = queue_in[k];
+#endif
             float4 ro = rays[2 * (size_t)pid], rd = rays[2 * (size_t)pid + 1];
             float4 h = hits[pid];
             int gid = __float_as_int(h.w);
