@@ -799,7 +799,7 @@ __device__ __forceinline__ bool quant_planes(float o, float scale, float lo, flo
 // leaf-order triangle record (common.cuh): 32 B (p0.xyz, p1.xyz, p2.xy) + 8 B (p2.z, global id)
 __device__ __forceinline__ void write_tri(const float4* __restrict__ verts, uint32_t t, uint32_t k, uint4* out_a,
                                           float2* out_b) {
-    const float4 a = verts[3ull * t], b = verts[3ull * t + 1], c = verts[3ull * t + 2];
+    const float4 a = __ldg(verts + 3ull * t), b = __ldg(verts + 3ull * t + 1), c = __ldg(verts + 3ull * t + 2);
     out_a[2ull * k] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(b.x));
     out_a[2ull * k + 1] = make_uint4(__float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(c.x), __float_as_uint(c.y));
     out_b[k] = make_float2(c.z, a.w);
@@ -815,14 +815,14 @@ __device__ __forceinline__ void write_leaf_tris(const float4* __restrict__ verts
     int cur = x;
     while (true) {
         if (cur >= n - 1) {
-            uint32_t t = vals[cur - (n - 1)];
+            uint32_t t = __ldg(vals + (cur - (n - 1)));
             write_tri(verts, t, k, out_a, out_b);
             ++k;
             if (sp == 0) break;
             cur = stack[--sp];
         } else {
-            if (sp < 16) stack[sp++] = right[cur];
-            cur = left[cur];
+            if (sp < 16) stack[sp++] = __ldg(right + cur);
+            cur = __ldg(left + cur);
         }
     }
 }
@@ -879,29 +879,53 @@ __device__ __forceinline__ void write_record(Node64* out, const float o[3], cons
     p[3] = make_uint4(ref[0], ref[1], ref[2], ref[3]);
 }
 
-__device__ __forceinline__ void emit_record(const EmitArgs& A, unsigned int idx) {
+// Everything emit reads except the queue is constant during the launch: __ldg loads, issued in batches (all
+// children at once), so that a record costs ~12 dependent memory round trips instead of ~30 (the stores to the
+// node / triangle arrays may alias the inputs as far as the compiler knows, which serialised every load behind
+// the store before it: emit was 0.38 ms of a 1.55 ms build at 1M triangles, 65 us per record per thread).
+// Called by whole warps (`active`: this lane has a record): the queue and triangle ranges of the warp's records
+// are reserved with ONE 64-bit atomic on the (queue tail, triangle tail) pair -- with one atomic pair per record
+// the two counters were the limit of the launch (9.8 M same-address atomics in 2.3 ms at 10M triangles).
+__device__ __forceinline__ void emit_record(const EmitArgs& A, unsigned int idx, bool active) {
     const int n = A.n;
-    const int v = A.queue[idx];
+    const int v = active ? A.queue[idx] : 0;
     int ch[4];
     int nc = 2;
-    ch[0] = A.left[v];
-    ch[1] = A.right[v];
+    ch[0] = __ldg(A.left + v);
+    ch[1] = __ldg(A.right + v);
+    const float4 lo4 = __ldg(A.bmin + v), hi4 = __ldg(A.bmax + v);
+    // per child: box, surface area (bmax.w), triangle count, "is a leaf of the wide tree"
+    float4 cl[4], chh[4];
+    uint32_t ctc[4];
+    bool leaf[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        cl[k] = __ldg(A.bmin + ch[k]); chh[k] = __ldg(A.bmax + ch[k]);
+        ctc[k] = __ldg(A.tcount + ch[k]);
+        leaf[k] = ch[k] >= n - 1 || __ldg(A.collapsed + ch[k]) != 0;
+    }
+#pragma unroll
     for (int it = 0; it < 2; ++it) {
         int best = -1;
         float ba = -1.0f;
-        for (int k = 0; k < nc; ++k) {
-            const int c = ch[k];
-            if (c < n - 1 && !A.collapsed[c]) {
-                const float sa = A.bmax[c].w;
-                if (sa > ba) { ba = sa; best = k; }
-            }
-        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < nc && !leaf[k] && chh[k].w > ba) { ba = chh[k].w; best = k; }
         if (best < 0) break;
-        const int c = ch[best];
-        ch[best] = A.left[c];
-        ch[nc++] = A.right[c];
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k == best) c = ch[k];
+        const int c0 = __ldg(A.left + c), c1 = __ldg(A.right + c);
+        const float4 l0 = __ldg(A.bmin + c0), h0 = __ldg(A.bmax + c0), l1 = __ldg(A.bmin + c1), h1 = __ldg(A.bmax + c1);
+        const uint32_t t0 = __ldg(A.tcount + c0), t1 = __ldg(A.tcount + c1);
+        const bool f0 = c0 >= n - 1 || __ldg(A.collapsed + c0) != 0, f1 = c1 >= n - 1 || __ldg(A.collapsed + c1) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k == best) { ch[k] = c0; cl[k] = l0; chh[k] = h0; ctc[k] = t0; leaf[k] = f0; }
+            if (k == nc) { ch[k] = c1; cl[k] = l1; chh[k] = h1; ctc[k] = t1; leaf[k] = f1; }
+        }
+        ++nc;
     }
-    const float4 lo4 = A.bmin[v], hi4 = A.bmax[v];
     const float o[3] = {lo4.x, lo4.y, lo4.z};
     const float ext[3] = {hi4.x - lo4.x, hi4.y - lo4.y, hi4.z - lo4.z};
     float clo[4][3], chi[4][3];
@@ -909,28 +933,68 @@ __device__ __forceinline__ void emit_record(const EmitArgs& A, unsigned int idx)
     // siblings get adjacent record slots and adjacent triangle ranges (one reservation each):
     // a ray that enters two children of this record finds the second one in the same lines
     uint32_t n_int = 0, n_tri = 0;
-    bool leaf[4];
-    for (int k = 0; k < nc; ++k) {
-        const int c = ch[k];
-        leaf[k] = c >= n - 1 || A.collapsed[c];
-        if (leaf[k]) n_tri += A.tcount[c];
-        else ++n_int;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nc) {
+            if (leaf[k]) n_tri += ctc[k];
+            else ++n_int;
+        }
     }
-    uint32_t pos = n_int ? atomicAdd(A.queue_tail, n_int) : 0u;
-    uint32_t start = n_tri ? atomicAdd(A.tri_tail, n_tri) : 0u;
-    for (int k = 0; k < nc; ++k) {
-        const int c = ch[k];
-        const float4 l = A.bmin[c], h = A.bmax[c];
-        clo[k][0] = l.x; clo[k][1] = l.y; clo[k][2] = l.z;
-        chi[k][0] = h.x; chi[k][1] = h.y; chi[k][2] = h.z;
-        if (leaf[k]) {
-            const uint32_t cnt = A.tcount[c];
-            write_leaf_tris(A.verts, A.vals, A.left, A.right, n, c, start, A.tri_a, A.tri_b);
-            ref[k] = kLeafFlag | (start << 3) | cnt;
-            start += cnt;
-        } else {
-            A.queue[pos] = c;
-            ref[k] = pos++;
+    // one-triangle leaves (the common case): triangle ids and vertices of all of them fetched together
+    uint32_t tid1[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < nc && ch[k] >= n - 1) tid1[k] = __ldg(A.vals + (ch[k] - (n - 1)));
+    float4 va[4], vb[4], vc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < nc && ch[k] >= n - 1) {
+            va[k] = __ldg(A.verts + 3ull * tid1[k]); vb[k] = __ldg(A.verts + 3ull * tid1[k] + 1); vc[k] = __ldg(A.verts + 3ull * tid1[k] + 2);
+        }
+    if (!active) { n_int = 0; n_tri = 0; nc = 0; }
+    uint32_t pos, start;
+    {
+        const unsigned FULL = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        const uint32_t mine = n_int | (n_tri << 16);  // <= 4 and <= 28 per record: the warp's sums fit 16 bits each
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const uint32_t tot = __shfl_sync(FULL, incl, 31);
+        unsigned long long base = 0ull;
+        if (lane == 31 && tot)  // (queue_tail, tri_tail) are adjacent 32-bit counters, 8-byte aligned
+            base = atomicAdd(reinterpret_cast<unsigned long long*>(A.queue_tail),
+                             (unsigned long long)(tot & 0xffffu) | ((unsigned long long)(tot >> 16) << 32));
+        base = __shfl_sync(FULL, base, 31);
+        const uint32_t excl = incl - mine;
+        pos = (uint32_t)base + (excl & 0xffffu);
+        start = (uint32_t)(base >> 32) + (excl >> 16);
+    }
+    if (!active) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nc) {
+            const int c = ch[k];
+            clo[k][0] = cl[k].x; clo[k][1] = cl[k].y; clo[k][2] = cl[k].z;
+            chi[k][0] = chh[k].x; chi[k][1] = chh[k].y; chi[k][2] = chh[k].z;
+            if (leaf[k]) {
+                const uint32_t cnt = ctc[k];
+                if (c >= n - 1) {
+                    A.tri_a[2ull * start] = make_uint4(__float_as_uint(va[k].x), __float_as_uint(va[k].y), __float_as_uint(va[k].z), __float_as_uint(vb[k].x));
+                    A.tri_a[2ull * start + 1] = make_uint4(__float_as_uint(vb[k].y), __float_as_uint(vb[k].z), __float_as_uint(vc[k].x), __float_as_uint(vc[k].y));
+                    A.tri_b[start] = make_float2(vc[k].z, va[k].w);
+                } else {
+                    write_leaf_tris(A.verts, A.vals, A.left, A.right, n, c, start, A.tri_a, A.tri_b);
+                }
+                ref[k] = kLeafFlag | (start << 3) | cnt;
+                start += cnt;
+            } else {
+                A.queue[pos] = c;
+                ref[k] = pos++;
+            }
         }
     }
     write_record(A.nodes + idx, o, ext, clo, chi, ref, nc);
@@ -940,7 +1004,10 @@ __device__ __forceinline__ void emit_record(const EmitArgs& A, unsigned int idx)
 // separates the levels, thread 0 publishes the next level's range in between.  Replaces one
 // emit + one advance launch per level (38 launches, 0.2 ms of gaps at 1M triangles).
 // level[0] = begin, level[1] = end of the current level in the queue, level[2] = depth so far.
-__global__ void __launch_bounds__(128)
+#ifndef PRT_EMIT_MIN_BLOCKS
+#define PRT_EMIT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, PRT_EMIT_MIN_BLOCKS)
 emit_levels_kernel(EmitArgs A, unsigned int* level, int max_levels) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -948,7 +1015,10 @@ emit_levels_kernel(EmitArgs A, unsigned int* level, int max_levels) {
     for (int lv = 0; lv < max_levels; ++lv) {
         const unsigned int begin = __ldcg(level), end = __ldcg(level + 1);
         if (begin >= end) break;  // (grid-uniform)
-        for (unsigned int idx = begin + tid; idx < end; idx += nthreads) emit_record(A, idx);
+        for (unsigned int base = begin + (tid & ~31u); base < end; base += nthreads) {  // (warp-uniform trip count)
+            const unsigned int idx = base + (tid & 31u);
+            emit_record(A, idx, idx < end);
+        }
         grid.sync();
         if (tid == 0) {
             const unsigned int tail = __ldcg(A.queue_tail);
