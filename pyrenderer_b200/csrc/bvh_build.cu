@@ -293,8 +293,8 @@ template <int NB>
 __device__ __forceinline__ void treelet_bins_clear(TreeletShared& S, int lane) {
     for (int k = lane; k < 3 * NB; k += 32) {
         int* bb = S.bins[k / NB][k % NB];
-        bb[0] = bb[1] = bb[2] = 0x7fffffff;              // f2ord(+inf) <= this
-        bb[3] = bb[4] = bb[5] = (int)0x80000000;
+        bb[0] = bb[1] = bb[2] = 0x7f800000;              // +inf (coordinates are >= +0: float bits order like ints)
+        bb[3] = bb[4] = bb[5] = 0;
         bb[6] = 0;
     }
 }
@@ -302,8 +302,8 @@ __device__ __forceinline__ void treelet_bins_clear(TreeletShared& S, int lane) {
 template <int NB>
 __device__ __forceinline__ uint32_t treelet_bin_add(TreeletShared& S, const float lo[3], const float hi[3],
                                                     const float cmin[3], const float scale[3]) {
-    const int l0 = f2ord(lo[0]), l1 = f2ord(lo[1]), l2 = f2ord(lo[2]);
-    const int h0 = f2ord(hi[0]), h1 = f2ord(hi[1]), h2 = f2ord(hi[2]);
+    const int l0 = __float_as_int(lo[0]), l1 = __float_as_int(lo[1]), l2 = __float_as_int(lo[2]);
+    const int h0 = __float_as_int(hi[0]), h1 = __float_as_int(hi[1]), h2 = __float_as_int(hi[2]);
     uint32_t pk = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -357,8 +357,8 @@ __device__ __forceinline__ float treelet_pick(TreeletShared& S, const float scal
             const int* bb = S.bins[a][bin];
             cnt = bb[6];
             if (cnt > 0) {
-                l0 = ord2f(bb[0]); l1 = ord2f(bb[1]); l2 = ord2f(bb[2]);
-                h0 = ord2f(bb[3]); h1 = ord2f(bb[4]); h2 = ord2f(bb[5]);
+                l0 = __int_as_float(bb[0]); l1 = __int_as_float(bb[1]); l2 = __int_as_float(bb[2]);
+                h0 = __int_as_float(bb[3]); h1 = __int_as_float(bb[4]); h2 = __int_as_float(bb[5]);
             }
         }
         // inclusive prefix (bins 0..bin) and suffix (bins bin..NB-1) within the NB-lane group
@@ -425,6 +425,11 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
         const int first = rg.x, m = rg.y - rg.x + 1;
         __syncwarp();
         // triangles of the subtree
+        // Boxes are kept RELATIVE to the subtree's min corner: every coordinate is >= +0, so float bits order like
+        // ints and the shared-memory atomics / REDUX below need no order-preserving conversion (54 of ~400
+        // instructions per split).  They only steer the SAH decisions; the boxes that are written out come from
+        // the vertices again (FUSED pass).
+        float tmin[3] = {inf, inf, inf};
         for (int k = lane; k < m; k += 32) {
             const uint32_t t = vals[first + k];
             float3 a, b;
@@ -433,6 +438,13 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
             S.hi[k][0] = b.x; S.hi[k][1] = b.y; S.hi[k][2] = b.z;
             S.tri[k] = t;
             S.order[k] = (uint8_t)k;
+            tmin[0] = fminf(tmin[0], a.x); tmin[1] = fminf(tmin[1], a.y); tmin[2] = fminf(tmin[2], a.z);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) tmin[a] = ord2f(__reduce_min_sync(FULL, f2ord(tmin[a])));
+        for (int k = lane; k < m; k += 32) {  // (each lane rewrites what it wrote)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { S.lo[k][a] -= tmin[a]; S.hi[k][a] -= tmin[a]; }
         }
         // internal node names inside the subtree: node i (first <= i <= last) whose range lies inside
         int n_names = 1;
@@ -476,9 +488,9 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const float cc = 0.5f * (lo[a] + hi[a]);  // (idle lanes: inf + -inf = NaN, replaced below)
-                    cmin[a] = ord2f(__reduce_min_sync(FULL, f2ord(has ? cc : inf)));
-                    cmax[a] = ord2f(__reduce_max_sync(FULL, f2ord(has ? cc : -inf)));
-                    scale[a] = cmax[a] > cmin[a] ? 8.0f / (cmax[a] - cmin[a]) : 0.0f;
+                    cmin[a] = __int_as_float(__reduce_min_sync(FULL, __float_as_int(has ? cc : inf)));
+                    cmax[a] = __int_as_float(__reduce_max_sync(FULL, __float_as_int(has ? cc : 0.0f)));
+                    scale[a] = cmax[a] > cmin[a] ? __fdividef(8.0f, cmax[a] - cmin[a]) : 0.0f;
                 }
                 uint32_t pk = 0;
                 int best_slot, nbs = 3;  // log2(bins)
@@ -523,14 +535,14 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
                 }
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {  // warp min / max through order-preserving ints (REDUX)
-                    cmin[a] = ord2f(__reduce_min_sync(FULL, f2ord(cmin[a])));
-                    cmax[a] = ord2f(__reduce_max_sync(FULL, f2ord(cmax[a])));
+                    cmin[a] = __int_as_float(__reduce_min_sync(FULL, __float_as_int(cmin[a])));
+                    cmax[a] = __int_as_float(__reduce_max_sync(FULL, __float_as_int(cmax[a])));  // (-inf of an idle lane: a negative int)
                 }
                 // 16 bins for the large ranges near the treelet root (8, one round, in the one-chunk path above)
                 constexpr int nb = 16;
                 float scale[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) scale[a] = cmax[a] > cmin[a] ? (float)nb / (cmax[a] - cmin[a]) : 0.0f;
+                for (int a = 0; a < 3; ++a) scale[a] = cmax[a] > cmin[a] ? __fdividef((float)nb, cmax[a] - cmin[a]) : 0.0f;
                 int best_slot;
                 treelet_best_split<16>(S, b, e, cmin, scale, lane, best_slot);
                 if (best_slot >= 0) {
@@ -595,8 +607,9 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
         if (FUSED) {
             // leaves of the subtree (what refit_kernel writes for a leaf), marked as covered
             for (int k = lane; k < m; k += 32) {
-                const int q = S.order[k], node = (n - 1) + first + k;
-                const float3 lo = make_float3(S.lo[q][0], S.lo[q][1], S.lo[q][2]), hi = make_float3(S.hi[q][0], S.hi[q][1], S.hi[q][2]);
+                const int node = (n - 1) + first + k;
+                float3 lo, hi;
+                tri_box(verts, S.tri[S.order[k]], lo, hi);
                 const float sa = box_area(lo, hi);
                 __stcg(O.bmin + node, make_float4(lo.x, lo.y, lo.z, P.ct * sa));
                 __stcg(O.bmax + node, make_float4(hi.x, hi.y, hi.z, sa));
@@ -640,18 +653,11 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
 #pragma unroll
                     for (int s2 = 0; s2 < 2; ++s2) {
                         const uint32_t cref = s2 ? plink >> 16 : plink & 0xffffu;
-                        if (cref & 0x8000u) {
-                            const int q = S.order[cref & 0x7fffu];
-                            const float3 lo = make_float3(S.lo[q][0], S.lo[q][1], S.lo[q][2]), hi = make_float3(S.hi[q][0], S.hi[q][1], S.hi[q][2]);
-                            const float sa = box_area(lo, hi);
-                            clo[s2] = make_float4(lo.x, lo.y, lo.z, P.ct * sa);
-                            chi[s2] = make_float4(hi.x, hi.y, hi.z, sa);
-                            ctc[s2] = 1u; cic[s2] = 0u;
-                        } else {
-                            const int cn = S.names[cref];
-                            clo[s2] = __ldcg(O.bmin + cn); chi[s2] = __ldcg(O.bmax + cn);
-                            ctc[s2] = __ldcg(O.tcount + cn); cic[s2] = __ldcg(O.icount + cn);
-                        }
+                        const bool is_leaf = (cref & 0x8000u) != 0u;
+                        const int cn = is_leaf ? (n - 1) + first + (int)(cref & 0x7fffu) : S.names[cref];
+                        clo[s2] = __ldcg(O.bmin + cn); chi[s2] = __ldcg(O.bmax + cn);  // (leaves: written above)
+                        ctc[s2] = is_leaf ? 1u : __ldcg(O.tcount + cn);
+                        cic[s2] = is_leaf ? 0u : __ldcg(O.icount + cn);
                     }
                     // (update_node, with the children in registers)
                     const float3 lo = make_float3(fminf(clo[0].x, clo[1].x), fminf(clo[0].y, clo[1].y), fminf(clo[0].z, clo[1].z));
