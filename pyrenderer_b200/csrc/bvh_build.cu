@@ -277,7 +277,7 @@ struct TreeletShared {
     int names[kTreelet];                      // internal node names available to this subtree; [0] = root
     uint32_t link[kTreelet];                  // per names index: children, 16 bits each (0x8000 | position = leaf, else names index)
     int stack[kTreeletStack][3];              // begin, end, names index
-    int bins[3][16][8];                       // per (axis, bin): ordered-int box lo.xyz, hi.xyz, count, pad
+    int bins[48][7];                          // per (axis * NB + bin): box lo.xyz, hi.xyz (float bits), count; odd stride: the (axis, bin) lanes hit different banks
 };
 
 __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
@@ -292,7 +292,7 @@ __device__ __forceinline__ float area3(const float lo[3], const float hi[3]) {
 template <int NB>
 __device__ __forceinline__ void treelet_bins_clear(TreeletShared& S, int lane) {
     for (int k = lane; k < 3 * NB; k += 32) {
-        int* bb = S.bins[k / NB][k % NB];
+        int* bb = S.bins[k];
         bb[0] = bb[1] = bb[2] = 0x7f800000;              // +inf (coordinates are >= +0: float bits order like ints)
         bb[3] = bb[4] = bb[5] = 0;
         bb[6] = 0;
@@ -311,7 +311,7 @@ __device__ __forceinline__ uint32_t treelet_bin_add(TreeletShared& S, const floa
         j = j > NB - 1 ? NB - 1 : j;
         pk |= (uint32_t)j << (8 * a);
         if (scale[a] > 0.0f) {
-            int* bb = S.bins[a][j];
+            int* bb = S.bins[a * NB + j];
             atomicMin(bb + 0, l0); atomicMin(bb + 1, l1); atomicMin(bb + 2, l2);
             atomicMax(bb + 3, h0); atomicMax(bb + 4, h1); atomicMax(bb + 5, h2);
             atomicAdd(bb + 6, 1);
@@ -354,7 +354,7 @@ __device__ __forceinline__ float treelet_pick(TreeletShared& S, const float scal
         float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
         int cnt = 0;
         if (sc_a > 0.0f) {
-            const int* bb = S.bins[a][bin];
+            const int* bb = S.bins[a * NB + bin];
             cnt = bb[6];
             if (cnt > 0) {
                 l0 = __int_as_float(bb[0]); l1 = __int_as_float(bb[1]); l2 = __int_as_float(bb[2]);
@@ -408,8 +408,11 @@ struct TreeletOut {
     uint8_t* collapsed;
 };
 
+#ifndef PRT_TREELET_MIN_BLOCKS
+#define PRT_TREELET_MIN_BLOCKS 7
+#endif
 template <bool FUSED>
-__global__ void __launch_bounds__(32 * kTreeletWarps)
+__global__ void __launch_bounds__(32 * kTreeletWarps, PRT_TREELET_MIN_BLOCKS)
 treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2* __restrict__ range,
                    int* left, int* right, int* parent, int n, const int* __restrict__ roots,
                    const unsigned int* __restrict__ n_roots, TreeletOut O, RefitParams P) {
@@ -1179,10 +1182,10 @@ static int build_once(prt_ctx* ctx, const prt_bvh_options& opt, prt_bvh_stats* s
     if (n > 2 && opt.treelets) {
         const TreeletOut O{B.bmin, B.bmax, B.tcount, B.icount, B.collapsed};
         if (fused)
-            treelet_sah_kernel<true><<<ctx->num_sms * 7, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
+            treelet_sah_kernel<true><<<ctx->num_sms * PRT_TREELET_MIN_BLOCKS, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
                                                                              B.parent, n, B.roots, B.n_roots, O, P);
         else
-            treelet_sah_kernel<false><<<ctx->num_sms * 7, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
+            treelet_sah_kernel<false><<<ctx->num_sms * PRT_TREELET_MIN_BLOCKS, 32 * kTreeletWarps>>>(ctx->verts_gid, B.vals[sorted], B.range, B.left, B.right,
                                                                               B.parent, n, B.roots, B.n_roots, O, P);
     }
     cudaEventRecord(ev[3]);
