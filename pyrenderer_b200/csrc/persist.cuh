@@ -33,6 +33,10 @@
 #define PRT_VISITS_PER_ITER 3  // record visits between two rounds of warp votes (profiles/r1_sweeps.txt)
 #endif
 
+#ifndef PRT_RAY_PREFETCH
+#define PRT_RAY_PREFETCH 1  // L2 prefetch of a reserved chunk's ray records (contiguous IO only)
+#endif
+
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 8  // __launch_bounds__ min blocks/SM of the persistent traversal kernels: caps ptxas at 64 registers
 #endif
@@ -137,6 +141,9 @@ __device__ __forceinline__ void trace_persistent(const SceneDev& sc, IO io, unsi
                 r_next = pb + (nidle - rem);
                 r_end = pb + chunk;
                 if (lane == 0) p_base = atomicAdd(fetch, chunk);
+#if PRT_RAY_PREFETCH
+                if ((unsigned)lane < chunk && pb + lane < n) io.prefetch(pb + lane);  // the chunk just entered: its rays are fetched over the next refills
+#endif
             } else {
                 r_next += nidle;
             }

@@ -159,6 +159,9 @@ struct ApiIO {
         }
         tag = k;
     }
+    __device__ __forceinline__ void prefetch(unsigned k) const {
+        if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + 2ull * k));
+    }
     __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
         if (MODE == MODE_CLOSEST)
             __stcs(reinterpret_cast<float4*>(out) + tag, make_float4(gid >= 0 ? t : 0.0f, u, v, __int_as_float(gid)));

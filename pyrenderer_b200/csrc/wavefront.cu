@@ -168,6 +168,7 @@ struct QueueClosestIO {
         tag = queue[k];
         ldg256_cs(rays + 2 * (size_t)tag, ro, rd);  // wave buffers are cudaMalloc'd: 32-byte aligned
     }
+    __device__ __forceinline__ void prefetch(unsigned) const {}
     __device__ __forceinline__ void store(uint32_t tag, float t, float u, float v, int gid) const {
         hits[tag] = make_float4(t, u, v, __int_as_float(gid));
     }
@@ -196,6 +197,9 @@ struct QueueShadowIO {
     __device__ __forceinline__ void load(unsigned k, float4& ro, float4& rd, uint32_t& tag) const {
         tag = k;
         ldg256_cs(srays + 2 * (size_t)k, ro, rd);
+    }
+    __device__ __forceinline__ void prefetch(unsigned k) const {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(srays + 2 * (size_t)k));
     }
     __device__ __forceinline__ void store(uint32_t tag, float, float, float, int gid) const {
         if (gid < 0) {
