@@ -18,3 +18,9 @@ d=json.load(open(sys.argv[1]))
 print(f"{sys.argv[1]:38s} {d['duration_ns']/1e6:7.3f} ms  dram {d['dram_bytes']/1e9:6.3f} GB ({d.get('dram_throughput_pct',0):4.1f} %)  L1 pipe {d.get('l1_data_pipe_pct',0):4.1f} %  L2 {d.get('l2_throughput_pct',0):4.1f} %  issue {d.get('issue_active_pct',0):4.1f} %  lanes {d.get('lanes_per_instruction',0):4.1f}  occ {d.get('occupancy_pct',0):4.1f} %  regs {d.get('registers',0):.0f}  L2 hit {d.get('l2_hit_pct',0):4.1f} %")
 PY
 done
+# the --page details text of the same captures
+for p in soup1m_exact soup1m_fp32 soup10m_fp32 cornell_closest cornell_shade; do
+  ncu -i $R/prof_$p.ncu-rep --page details 2>/dev/null | grep -v -e '^ *-\{5,\}' -e '^ *$' > profiles/r2_${p}_ncu.txt
+done
+cp $R/bench_launches.csv profiles/r2_bench_launches.csv
+python profiles/summarize_launches.py $R/bench_launches.csv > profiles/r2_bench_launches.txt
