@@ -249,6 +249,9 @@ struct RefitParams {
 #endif
 constexpr int kTreelet = PRT_TREELET;  // <= 255 (8-bit permutation)
 constexpr int kTreeletWarps = 4;  // warps per block
+#ifndef PRT_TREELET_ENUM
+#define PRT_TREELET_ENUM 1  // ranges of 3 / 4 triangles: exact SAH over all 3 / 7 partitions
+#endif
 #ifndef PRT_TREELET_FINE
 #define PRT_TREELET_FINE 32  // one-chunk ranges with more triangles than this use 16 bins instead of 8
 #endif
@@ -476,6 +479,46 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
             const int c = e - b;
             __syncwarp();
             int mid = b + 1;
+#if PRT_TREELET_ENUM
+            if (c == 3 || c == 4) {
+                // ---- 3 or 4 triangles (a third of all splits): the 3 (1|2) or 7 (1|3, 2|2) ways to split the set are
+                // costed exactly, one per lane, instead of going through bins, atomics and scans
+                float lo[4][3], hi[4][3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int qi = S.order[b + (i < c ? i : 0)];  // (broadcast loads)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { lo[i][a] = S.lo[qi][a]; hi[i][a] = S.hi[qi][a]; }
+                }
+                const int myq = S.order[b + (lane < c ? lane : 0)];
+                const unsigned lmask = lane < 4 ? 1u << lane : (1u | (1u << (lane - 3)));  // lanes 4..6: {0,1} {0,2} {0,3}
+                const bool valid = c == 3 ? lane < 3 : lane < 7;
+                float ll[3] = {inf, inf, inf}, lh[3] = {-inf, -inf, -inf}, rl[3] = {inf, inf, inf}, rh[3] = {-inf, -inf, -inf};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < c) {
+                        const bool in = (lmask >> i) & 1u;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            ll[a] = fminf(ll[a], in ? lo[i][a] : inf); lh[a] = fmaxf(lh[a], in ? hi[i][a] : -inf);
+                            rl[a] = fminf(rl[a], in ? inf : lo[i][a]); rh[a] = fmaxf(rh[a], in ? -inf : hi[i][a]);
+                        }
+                    }
+                }
+                const int nl = __popc(lmask);
+                const float cost = valid ? area3(ll, lh) * (float)nl + area3(rl, rh) * (float)(c - nl) : inf;
+                const unsigned key = __float_as_uint(cost);  // (costs are >= 0: bit patterns order like unsigned integers)
+                const unsigned kmin = __reduce_min_sync(FULL, key);
+                const int win = __reduce_min_sync(FULL, (valid && key == kmin) ? lane : 31);
+                const unsigned wmask = __shfl_sync(FULL, lmask, win);
+                const int wl = __popc(wmask);
+                const unsigned below = (1u << lane) - 1u;
+                const int pos = ((wmask >> lane) & 1u) ? __popc(wmask & below) : wl + __popc(~wmask & below);
+                __syncwarp();
+                if (lane < c) S.order[b + pos] = (uint8_t)myq;  // stable on both sides
+                mid = b + wl;
+            } else
+#endif
             if (c > 2 && c <= 32) {
                 // ---- one triangle per lane: box, centroid and bins stay in registers from the centroid bounds to the
                 // partition (most splits of a subtree are of this size; same bins, same plane, same order as below)
