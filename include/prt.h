@@ -161,9 +161,13 @@ typedef struct {
     uint32_t max_leaf_tris; /* 1..7, default 4 */
     float cost_node;        /* SAH traversal cost, default 1.0 */
     float cost_tri;         /* SAH intersection cost, default 2.0 */
-    uint32_t rotations;     /* number of bottom-up SAH rotation passes during refit (0 = none, default 1) */
+    uint32_t rotations;     /* number of bottom-up SAH rotation passes during refit (0 = none, default 1).
+                               With treelets and <= 1 pass the rebuilt subtrees are refitted by the warp that
+                               built them and rotations apply above them only; > 1 re-derives every pass from
+                               the leaves */
     uint32_t treelets;      /* 1 (default): every maximal subtree of <= 128 triangles of the Morton
-                               hierarchy is rebuilt with binned SAH before refit; 0 = plain LBVH */
+                               hierarchy is rebuilt with SAH (exact for <= 6 triangles, binned above) before
+                               refit; 0 = plain LBVH */
     uint32_t morton_bits;   /* 30, 63, or 0 (default) = 30 unless more than 1/16 of the sorted neighbours
                                share a 30-bit cell (clustered geometry), then 63 (21 bits per axis) */
 } prt_bvh_options;

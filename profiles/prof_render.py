@@ -1,6 +1,6 @@
 """Small driver for ncu: Cornell 1024x1024, depth 8, 16 spp waves (the bench's headline frame is 64 of them).
 Prints the number of rays of every bounce (closest / shadow) so that a captured launch can be normalised per ray.
-usage: python profiles/prof_render.py [n_waves] [classes]"""
+usage: python profiles/prof_render.py [n_waves] [classes] [bvh option=value ...]"""
 import json
 import os
 import sys
@@ -13,7 +13,10 @@ from pyrenderer_b200 import _abi  # noqa: E402
 
 n_waves = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scene, cam = load_cornell()
-ctx = scene.commit(0)
+bvh_kw = {a.split("=")[0]: float(a.split("=")[1]) for a in sys.argv[3:] if "=" in a}  # e.g. max_leaf_tris=7 cost_tri=1
+ctx = scene.commit(0, **bvh_kw)
+if bvh_kw:
+    print("bvh", bvh_kw, {k: scene.bvh_stats[k] for k in ("n_nodes", "depth", "sah_cost")})
 ctx.set_camera(*cam.device_record())
 W, H = cam.get_resolution()
 acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")

@@ -9,10 +9,14 @@
 //                        63-bit keys: low word first, then the high word (stable)
 //   4. hierarchy_kernel  Karras 2012 "Maximizing parallelism in the construction
 //                        of BVHs, octrees and k-d trees": one thread per internal node
-//   5. refit_kernel      bottom-up with arrival flags: boxes, SAH cost, SAH tree
-//                        rotations (3-leaf treelets) and SAH leaf collapse (<= 7 tris)
+//   5. treelet_sah_kernel one warp per maximal subtree of <= 128 triangles: top-down SAH rebuild in shared
+//                        memory (exact enumeration for 3..6 triangles, 8 / 16 bins above), then the warp
+//                        refits its own subtree (boxes, SAH cost, leaf collapse, counts)
+//      refit_kernel      bottom-up with arrival flags from the subtree ROOTS (and the leaves no subtree
+//                        covers): boxes, SAH cost, SAH tree rotations and SAH leaf collapse (<= 7 tris)
 //   6. emit_levels_kernel breadth-first collapse of the binary tree into 4-wide records, ONE
-//                        cooperative launch (grid-wide barrier between levels)
+//                        cooperative launch (grid-wide barrier between levels), one 64-bit atomic
+//                        per warp for the record / triangle reservations
 //                        (expand the child of largest surface area), conservative 8-bit
 //                        quantisation of the child boxes in the record's frame, leaf
 //                        triangles copied to contiguous ranges
@@ -243,15 +247,20 @@ struct RefitParams {
 // x 3 axes) by one warp, entirely in shared memory; it reuses the subtree's own node names and
 // its own range of sorted positions, so nothing outside the subtree changes.  Measured on the
 // 1M-triangle soup (profiles/bvh_quality.c): record visits per ray 39.5 -> 37.8 (64) .. 37.4 (256), most of what a
-// full SAH build would give (37.2).  Runs before refit (boxes, rotations, collapse come after).
+// full SAH build would give (37.2).  The kernel is instruction- and shared-memory-bound (profiles/r2_sweeps.txt):
+// what made it faster were fewer instructions per split (ranges of <= 32 triangles kept in registers, ranges
+// of <= 6 enumerated) and conflict-free bin rows, not more warps or shorter dependency chains.
 #ifndef PRT_TREELET
 #define PRT_TREELET 128
 #endif
 constexpr int kTreelet = PRT_TREELET;  // <= 255 (8-bit permutation)
 constexpr int kTreeletWarps = 4;  // warps per block
 #ifndef PRT_TREELET_ENUM
-#define PRT_TREELET_ENUM 1  // ranges of 3 / 4 triangles: exact SAH over all 3 / 7 partitions
+#define PRT_TREELET_ENUM 1  // ranges of 3 .. 6 triangles: exact SAH over all their two-way partitions
 #endif
+// lane -> its candidate left set among the 3 / 7 / 15 / 31 two-way partitions of 3 / 4 / 5 / 6 items (6 bits each,
+// packed c = 3 first): every subset of at most half the items; of the halves, those that contain item 0
+__device__ const uint32_t kEnumMasks[32] = {0x041041u, 0x082082u, 0x104104u, 0x208200u, 0x4100c0u, 0x803140u, 0x0c5240u, 0x149000u, 0x251000u, 0x446000u, 0x84a000u, 0x192000u, 0x28c000u, 0x494000u, 0x898000u, 0x300000u, 0x500000u, 0x900000u, 0x600000u, 0xa00000u, 0xc00000u, 0x1c0000u, 0x2c0000u, 0x4c0000u, 0x8c0000u, 0x340000u, 0x540000u, 0x940000u, 0x640000u, 0xa40000u, 0xc40000u, 0x000000u};
 #ifndef PRT_TREELET_FINE
 #define PRT_TREELET_FINE 32  // one-chunk ranges with more triangles than this use 16 bins instead of 8
 #endif
@@ -425,6 +434,7 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
     const unsigned FULL = 0xffffffffu;
     const unsigned nr = *n_roots;
     const float inf = __int_as_float(0x7f800000);
+    const uint32_t enum_masks = kEnumMasks[lane];
     for (unsigned ri = blockIdx.x * kTreeletWarps + (threadIdx.x >> 5); ri < nr; ri += gridDim.x * kTreeletWarps) {
         const int root = roots[ri];
         const int2 rg = range[root];
@@ -480,36 +490,30 @@ treelet_sah_kernel(const float4* __restrict__ verts, uint32_t* vals, const int2*
             __syncwarp();
             int mid = b + 1;
 #if PRT_TREELET_ENUM
-            if (c == 3 || c == 4) {
-                // ---- 3 or 4 triangles (a third of all splits): the 3 (1|2) or 7 (1|3, 2|2) ways to split the set are
-                // costed exactly, one per lane, instead of going through bins, atomics and scans
-                float lo[4][3], hi[4][3];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int qi = S.order[b + (i < c ? i : 0)];  // (broadcast loads)
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) { lo[i][a] = S.lo[qi][a]; hi[i][a] = S.hi[qi][a]; }
-                }
-                const int myq = S.order[b + (lane < c ? lane : 0)];
-                const unsigned lmask = lane < 4 ? 1u << lane : (1u | (1u << (lane - 3)));  // lanes 4..6: {0,1} {0,2} {0,3}
-                const bool valid = c == 3 ? lane < 3 : lane < 7;
+            if (c <= 6 && c > 2) {
+                // ---- 3 .. 6 triangles (40 % of all splits): every way to split the set in two -- 3, 7, 15 or 31 of them,
+                // kEnumMasks -- is costed exactly, one per lane, instead of going through bins, atomics and scans
+                const unsigned lmask = (enum_masks >> (6 * (c - 3))) & 63u;  // this lane's left set (0: no candidate)
                 float ll[3] = {inf, inf, inf}, lh[3] = {-inf, -inf, -inf}, rl[3] = {inf, inf, inf}, rh[3] = {-inf, -inf, -inf};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 6; ++i) {
                     if (i < c) {
+                        const int qi = S.order[b + i];  // (broadcast loads)
                         const bool in = (lmask >> i) & 1u;
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
-                            ll[a] = fminf(ll[a], in ? lo[i][a] : inf); lh[a] = fmaxf(lh[a], in ? hi[i][a] : -inf);
-                            rl[a] = fminf(rl[a], in ? inf : lo[i][a]); rh[a] = fmaxf(rh[a], in ? -inf : hi[i][a]);
+                            const float l = S.lo[qi][a], h = S.hi[qi][a];
+                            ll[a] = fminf(ll[a], in ? l : inf); lh[a] = fmaxf(lh[a], in ? h : -inf);
+                            rl[a] = fminf(rl[a], in ? inf : l); rh[a] = fmaxf(rh[a], in ? -inf : h);
                         }
                     }
                 }
+                const int myq = S.order[b + (lane < c ? lane : 0)];
                 const int nl = __popc(lmask);
-                const float cost = valid ? area3(ll, lh) * (float)nl + area3(rl, rh) * (float)(c - nl) : inf;
+                const float cost = lmask ? area3(ll, lh) * (float)nl + area3(rl, rh) * (float)(c - nl) : inf;
                 const unsigned key = __float_as_uint(cost);  // (costs are >= 0: bit patterns order like unsigned integers)
                 const unsigned kmin = __reduce_min_sync(FULL, key);
-                const int win = __reduce_min_sync(FULL, (valid && key == kmin) ? lane : 31);
+                const int win = __reduce_min_sync(FULL, (lmask && key == kmin) ? lane : 31);
                 const unsigned wmask = __shfl_sync(FULL, lmask, win);
                 const int wl = __popc(wmask);
                 const unsigned below = (1u << lane) - 1u;
