@@ -461,6 +461,67 @@ def test_fuzz_small_scenes_exact_ids(gpu_ctx):
         assert np.sum(ids_f != ids_o) <= 1, f"fuzz{nt}/{kind}: plain FP32 mismatches {np.sum(ids_f != ids_o)} of 1500"
 
 
+def test_builder_paths_against_the_exhaustive_walk(gpu_ctx):
+    """Every path of the builder -- treelet warps that refit their own subtree (default) and the unfused
+    refit from the leaves (rotations = 2, treelets = 0), exact enumeration of 3..6-triangle ranges, the
+    one-chunk and the 16-bin split, the warp-aggregated emit -- on soups, clusters, coplanar grids with
+    duplicates and mixed scales with degenerate triangles: ids AND t of the EXACT BVH traversal equal the
+    exhaustive EXACT walk over all triangles (same tests, no BVH), and a rebuild gives the same tree size."""
+    torch = _torch()
+    rng = np.random.default_rng(99)
+
+    def scene(nt, kind):
+        if kind == 0:
+            return random_soup(nt, seed=nt)
+        if kind == 1:  # clusters
+            k = max(1, nt // 300)
+            cen = rng.uniform(0, 1, (k, 1, 3))
+            return (cen[rng.integers(0, k, nt)] + rng.normal(0, 0.003, (nt, 3, 3))).astype(np.float32)
+        if kind == 2:  # coplanar quads split in two, an eighth of them duplicated
+            m = int(np.ceil(np.sqrt(nt / 2))) + 1
+            xs = np.linspace(0, 1, m + 1, dtype=np.float32)
+            i, j = np.meshgrid(np.arange(m), np.arange(m), indexing="ij")
+            a = np.stack([xs[i], xs[j], np.full_like(xs[i], 0.5)], -1).reshape(-1, 3)
+            b = np.stack([xs[i + 1], xs[j], np.full_like(xs[i], 0.5)], -1).reshape(-1, 3)
+            c = np.stack([xs[i + 1], xs[j + 1], np.full_like(xs[i], 0.5)], -1).reshape(-1, 3)
+            d = np.stack([xs[i], xs[j + 1], np.full_like(xs[i], 0.5)], -1).reshape(-1, 3)
+            t = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], 0)[:nt].astype(np.float32)
+            if nt > 8:
+                t[rng.integers(0, nt, nt // 8)] = t[rng.integers(0, nt, nt // 8)]
+            return t
+        t = random_soup(nt, seed=3 * nt)  # mixed scales + zero-area triangles
+        big = rng.integers(0, nt, max(1, nt // 50))
+        t[big] = rng.uniform(-2, 3, (big.size, 3, 3)).astype(np.float32)
+        deg = rng.integers(0, nt, max(1, nt // 40))
+        t[deg, 2] = t[deg, 1]
+        return t
+
+    option_sets = [dict(), dict(max_leaf_tris=1), dict(max_leaf_tris=7, cost_tri=0.5), dict(rotations=0),
+                   dict(rotations=2), dict(treelets=0)]
+    sizes = [3, 4, 5, 6, 7, 9, 33, 127, 130, 700, 4097, 20000, 50000]
+    for k, nt in enumerate(sizes):
+        for kind in range(4):
+            tris = scene(nt, kind)
+            nr = 4096
+            rays = random_rays(nr, seed=1000 + nt + kind)
+            rays[: nr // 4, 6] = 0.0  # a quarter of the directions lie in a coordinate plane
+            rays[:, 4:7] /= np.maximum(np.linalg.norm(rays[:, 4:7], axis=1, keepdims=True), 1e-20)
+            r = torch.from_numpy(rays).cuda()
+            opts = option_sets[(k + kind) % len(option_sets)]
+            gpu_ctx.set_triangles(tris)
+            st = gpu_ctx.build_bvh(**opts)
+            assert st["n_tris"] == nt and 3 * st["depth"] + 1 <= 128 and st["morton_sorted"] == 1, (nt, kind, opts, st)
+            hb = torch.empty((nr, 4), dtype=torch.float32, device="cuda")
+            hx = torch.empty_like(hb)
+            gpu_ctx.trace_closest(r, nr, hb, EXACT | BRUTE)
+            gpu_ctx.trace_closest(r, nr, hx, EXACT)
+            torch.cuda.synchronize()
+            assert torch.equal(hb[:, 3].view(torch.int32), hx[:, 3].view(torch.int32)), (nt, kind, opts)
+            assert torch.equal(hb[:, 0], hx[:, 0]), (nt, kind, opts)
+            st2 = gpu_ctx.build_bvh(**opts)  # same input, same options: same tree size and cost
+            assert st2["n_nodes"] == st["n_nodes"] and st2["sah_cost"] == st["sah_cost"], (nt, kind, opts)
+
+
 def test_morton_63_bit_keys_and_grow_only_buffers(gpu_ctx):
     """63-bit Morton keys (21 bits per axis): picked automatically when the 30-bit grid cannot
     separate the triangles (a dense cluster inside a huge scene box), selectable by hand, and
