@@ -511,7 +511,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": c3_workload(total), "spp_per_rank": [tracing.shard_samples(total, r, world)[1] - tracing.shard_samples(total, r, world)[0] for r in range(world)],
                        "exact_primary": True, "estimator": "reference (core/tracing.py:116-155)", "rng": "Philox4x32-10 per (pixel, sample, bounce)",
-                       "l2": f"inputs larger than L2: every 16-spp wave streams {16 * W * H * 136 / 2**30:.1f} GiB of path state",
+                       "l2": f"inputs larger than L2: every wave (64 spp of every pixel) streams {64 * W * H * 136 / 2**30:.1f} GiB of path state",
                        "api": "pyrenderer_b200.core.tracing.render_distributed -> prt_render_sharded" if world > 1 else
                               "pyrenderer_b200.core.tracing.render_distributed -> prt_render",
                        "bvh": scene.bvh_stats},

@@ -281,7 +281,8 @@ int prt_eval_specular(prt_ctx* ctx, const prt_bsdf_query* queries_dev, uint64_t 
  * everything that is scratch (build arena, host-call staging, exact-mode flag lists, wavefront
  * state); the scene and its BVH stay usable. */
 int prt_release_scratch(prt_ctx* ctx);
-/* paths per wavefront wave (default 16 Mi = 2.2 GB of path state); 0 keeps the current value */
+/* paths per wavefront wave (default 64 Mi = 8.5 GiB of path state, allocated only as far as a render needs it:
+ * width * height * min(spp, wave / pixels) paths); 0 keeps the current value */
 int prt_set_wave_paths(prt_ctx* ctx, uint64_t paths);
 
 /* ---- multi-GPU: sample-sharded render over a replicated scene + BVH (one process per GPU) ----

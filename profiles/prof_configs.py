@@ -1,5 +1,5 @@
 """BASELINE configs 4 (10M soup) and 5 (subdivided Cornell, 4K) on one B200.
-usage: python profiles/prof_configs.py c4 | c5"""
+usage: python profiles/prof_configs.py c4 | c5 [spp per render] [Mi paths per wave]"""
 import os, sys, json
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -53,7 +53,9 @@ else:
     W, H = 3840, 2160
     ctx.set_camera(iview, sh * (W / H), sh, focal, W, H)
     acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    spp = 4
+    spp = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    if len(sys.argv) > 3:
+        ctx.set_wave_paths(int(sys.argv[3]) << 20)  # Mi paths per wave
     res = []
     for rep in range(3):
         ctx.reset_counters()

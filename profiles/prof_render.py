@@ -14,6 +14,7 @@ from pyrenderer_b200 import _abi  # noqa: E402
 n_waves = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scene, cam = load_cornell()
 bvh_kw = {a.split("=")[0]: float(a.split("=")[1]) for a in sys.argv[3:] if "=" in a}  # e.g. max_leaf_tris=7 cost_tri=1
+SPW = int(bvh_kw.pop("spp_wave", 16))  # samples per pixel per wave (16 = the library default of 2^24 paths at 1024^2)
 ctx = scene.commit(0, **bvh_kw)
 if bvh_kw:
     print("bvh", bvh_kw, {k: scene.bvh_stats[k] for k in ("n_nodes", "depth", "sah_cost")})
@@ -30,6 +31,8 @@ for depth in range(1, 9):  # rays per bounce: difference of the counters of dept
     prev = (c["rays_closest"], c["rays_shadow"])
 print(json.dumps({"rays_per_bounce_closest": [p[0] for p in per_bounce], "rays_per_bounce_shadow": [p[1] for p in per_bounce]}))
 torch.cuda.synchronize()
+if SPW != 16:
+    ctx.set_wave_paths(SPW * W * H)
 if len(sys.argv) > 2 and sys.argv[2] == "classes":  # per-kernel-class ms of n_waves 16-spp waves (cudaEvent pairs, best of 3)
     best = None
     for rep in range(3):
@@ -37,11 +40,11 @@ if len(sys.argv) > 2 and sys.argv[2] == "classes":  # per-kernel-class ms of n_w
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(n_waves):
-            ctx.render(ctx.render_params(seed=1, spp_begin=16 * k, spp_end=16 * k + 16, max_depth=8, flags=_abi.RENDER_EXACT_PRIMARY), acc)
+            ctx.render(ctx.render_params(seed=1, spp_begin=SPW * k, spp_end=SPW * k + SPW, max_depth=8, flags=_abi.RENDER_EXACT_PRIMARY), acc)
         e1.record()
         torch.cuda.synchronize()
-        prof = {k: round(v[0] / n_waves, 4) for k, v in ctx.profile_end().items()}
-        prof["wave_ms"] = round(e0.elapsed_time(e1) / n_waves, 4)
+        prof = {k: round(v[0] / n_waves * 16 / SPW, 4) for k, v in ctx.profile_end().items()}  # per 16 spp
+        prof["wave_ms"] = round(e0.elapsed_time(e1) / n_waves * 16 / SPW, 4)
         if best is None or prof["wave_ms"] < best["wave_ms"]:
             best = prof
     print(json.dumps(best))

@@ -57,7 +57,7 @@ struct prt_ctx {
     unsigned int* fetch_counters = nullptr;  // [kFetchRing] ray-fetch counters of persistent launches
     unsigned fetch_next = 0;
     int grid_persist = 0, grid_persist_exact = 0;  // resident CTAs of the plain / EXACT persistent kernels
-    int refill_idle = 0, leaf_batch = 8;  // refill_idle 0 = by scene size (profiles/r1_sweeps.txt)
+    int refill_idle = 0, leaf_batch = 0;  // 0 = by scene size (profiles/r1_sweeps.txt, r2_sweeps.txt)
     int fetch_chunk = 0;                  // ray indices reserved per atomic; 0 = default (32)
 
     // device staging of the *_host entry points (grow-only, reused across calls)
@@ -69,7 +69,7 @@ struct prt_ctx {
 
     // wavefront state (wavefront.cu)
     void* wf = nullptr;
-    uint64_t wave_paths = 16ull << 20;
+    uint64_t wave_paths = 64ull << 20;  // 8.5 GiB of path state; Cornell 1024^2 per 16 spp: 12.68 ms (16 Mi) / 12.31 (32 Mi) / 12.15 (64 Mi) / 12.06 (128 Mi)
     // multi-GPU (collective.cu): communicator, this rank, and the per-frame shard buffer
     void* comm = nullptr;  // ncclComm_t
     bool comm_owned = false;
@@ -106,9 +106,12 @@ struct prt_ctx {
         s.light_tris = light_tris;
         s.verts_gid = verts_gid;
         s.nt = nt; s.n_nodes = n_nodes; s.nl = nl; s.nm = nm;
-        // short traversals (tiny scenes) amortise the ray set-up over more lanes per refill
-        s.refill_idle = refill_idle > 0 ? refill_idle : (n_nodes < 4096 ? 16 : 6);
-        s.leaf_batch = leaf_batch;
+        // short traversals (tiny scenes) amortise the ray set-up over more lanes per refill and wait for more
+        // parked lanes before a leaf phase (Cornell 16-spp wave: refill / leaf 16 / 8 -> 12 / 16: 12.68 -> 12.50 ms;
+        // on the 1M soup a leaf batch of 16 costs 9 %)
+        const bool tiny = n_nodes < 4096;
+        s.refill_idle = refill_idle > 0 ? refill_idle : (tiny ? 12 : 6);
+        s.leaf_batch = leaf_batch > 0 ? leaf_batch : (tiny ? 16 : 8);
         // one warp's worth per atomic: larger chunks lengthen the end-of-launch tail (measured:
         // soup-1M 16..64 equal, 128 -0.6 %; Cornell 8 spp 32: 7.49 ms, 256: 7.99 ms, 1024: 13.4 ms)
         s.fetch_chunk = fetch_chunk > 0 ? fetch_chunk : 32;

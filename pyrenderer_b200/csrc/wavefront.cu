@@ -567,6 +567,10 @@ int render(prt_ctx* ctx, const prt_render_params* p, float* accum, int32_t* prim
     if (per_wave == 0) per_wave = 1;
     const uint32_t ns_total = p->spp_end - p->spp_begin;
     if (per_wave > ns_total) per_wave = ns_total;
+    {   // equal waves: 16 spp under a cap of 7 run as 6 + 6 + 4, not 7 + 7 + 2 (a small last wave runs at a fraction of the rate)
+        const uint64_t n_waves = (ns_total + per_wave - 1) / per_wave;
+        per_wave = (ns_total + n_waves - 1) / n_waves;
+    }
     int rc = wave_alloc(ctx, npix * per_wave);
     if (rc != PRT_OK) return rc;
     WaveState* w = (WaveState*)ctx->wf;
