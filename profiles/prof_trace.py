@@ -1,5 +1,5 @@
 """Small driver for ncu: N-triangle soup, closest-hit batches of 2^24 incoherent rays (= one bench.py step).
-usage: python profiles/prof_trace.py [n_launches] [exact|fp32] [n_tris]"""
+usage: python profiles/prof_trace.py [n_launches] [exact|fp32] [n_tris] [log2 rays per launch]"""
 import os
 import sys
 
@@ -13,7 +13,7 @@ from pyrenderer_b200 import _abi  # noqa: E402
 n_launch = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 flags = _abi.TRACE_EXACT if (len(sys.argv) > 2 and sys.argv[2] == "exact") else 0
 n_tris = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
-N = 1 << 24  # the bench launch: 2^24 rays
+N = 1 << (int(sys.argv[4]) if len(sys.argv) > 4 else 24)  # the bench launch: 2^24 rays
 dev = torch.device("cuda", 0)
 ctx = _abi.Context(0)
 ctx.set_triangles_dev(torch.from_numpy(soup(n_tris)).to(dev), n_tris)
