@@ -283,6 +283,47 @@ def test_any_and_all_hits(gpu_ctx):
     assert c["rays_closest"] == rays.shape[0] and c["node_visits"] > rays.shape[0] and c["tri_tests"] > 0
 
 
+def test_accept_rule_known_answers_on_the_gpu(gpu_ctx):
+    """The crafted cases of tests/test_oracle_golden.py::test_oracle_edge_cases_and_accept_rule through the C ABI:
+    rays through edges and vertices (inclusive), t exactly at tmin / tmax (inclusive), stacked identical triangles
+    (lowest id wins, the hit SET holds all of them), a quad's shared diagonal -- closest, any and all hits, BVH and
+    exhaustive walk, against the oracle."""
+    torch = _torch()
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], np.float32)
+    stack = np.concatenate([tri + np.float32([0, 0, -1]), tri, tri, tri + np.float32([0, 0, 0.5]), tri + np.float32([0, 0, 0.5])])
+    quad = np.array([[[0, 0, 0], [1, 0, 0], [1, 1, 0]], [[0, 0, 0], [1, 1, 0], [0, 1, 0]]], np.float32)
+    pts = [[0.25, 0.25], [0.5, 0.0], [0.0, 0.5], [0.5, 0.5], [0.0, 0.0], [1.0, 0.0], [0.0, 1.0],
+           [0.5, -1e-6], [-1e-6, 0.5], [0.5 + 1e-6, 0.5 + 1e-6]]
+    o = [[x, y, 1.0] for x, y in pts] + [[x, y, -2.0] for x, y in pts] + [[-1, 0.25, 0.0], [0.25, 0.25, 1.0]]
+    d = [[0, 0, -1]] * len(pts) + [[0, 0, 1]] * len(pts) + [[1, 0, 0], [0, 0, 1]]
+    rays = make_rays(o, d)
+    rng_t = make_rays([[0.25, 0.25, 1.0]] * 4, [[0, 0, -1]] * 4)
+    rng_t[:, 3] = [1.0, np.nextafter(np.float32(1.0), np.float32(2.0)), 0.0, 0.0]
+    rng_t[:, 7] = [9.0, 9.0, 1.0, np.nextafter(np.float32(1.0), np.float32(0.0))]
+    rays = np.concatenate([rays, rng_t])
+    for name, tris in (("tri", tri), ("stack", stack), ("quad", quad), ("quad-reversed", quad[::-1].copy())):
+        gpu_ctx.set_triangles(tris)
+        gpu_ctx.build_bvh()
+        ref = oracle.closest_hit(tris, rays)
+        assert np.any(ref[0] >= 0) and np.any(ref[0] < 0)
+        check_against_oracle(gpu_ctx, tris, rays, EXACT, f"accept/{name}", ref)
+        check_against_oracle(gpu_ctx, tris, rays, EXACT | BRUTE, f"accept/{name}/brute", ref)
+        r = torch.from_numpy(rays).cuda()
+        occ = torch.empty(rays.shape[0], dtype=torch.uint8, device="cuda")
+        cnt = torch.empty(rays.shape[0], dtype=torch.int32, device="cuda")
+        sums = torch.empty(rays.shape[0], dtype=torch.int64, device="cuda")
+        cnt_o, sums_o = oracle.all_hits(tris, rays)
+        for flags in (EXACT, EXACT | BRUTE):
+            gpu_ctx.trace_any(r, rays.shape[0], occ, flags)
+            gpu_ctx.trace_all(r, rays.shape[0], cnt, sums, flags)
+            torch.cuda.synchronize()
+            assert np.array_equal(occ.cpu().numpy().astype(bool), ref[0] >= 0), name
+            assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o), name
+            assert np.array_equal(sums.cpu().numpy().view(np.uint64), sums_o), name
+    ref = oracle.closest_hit(stack, rays)
+    assert ref[0][0] == 3 and ref[0][len(pts)] == 0  # from above: the lower id of the two at z = 0.5; from below: id 0
+
+
 def test_edge_cases(gpu_ctx, cornell):
     torch = _torch()
     # empty scene

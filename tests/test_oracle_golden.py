@@ -207,3 +207,91 @@ def test_specular_bsdfs_match_bsdf_taichi(rad_golden):
     sin_t = np.linalg.norm(t - np.sum(t * n[ok], 1)[:, None] * n[ok], axis=1)
     assert np.allclose(sin_t, eta[ok] * sin_i[ok], atol=1e-13) and np.allclose(np.linalg.norm(t, axis=1), 1.0, atol=1e-13)
     assert np.all(np.sum(t * n[ok], 1) < 0)
+
+
+def _rays(o, d, tmin=1e-5, tmax=3.4e38):
+    o = np.asarray(o, np.float32).reshape(-1, 3)
+    d = np.asarray(d, np.float32).reshape(-1, 3)
+    r = np.empty((o.shape[0], 8), np.float32)
+    r[:, 0:3], r[:, 3], r[:, 4:7], r[:, 7] = o, tmin, d, tmax
+    return r
+
+
+def test_oracle_edge_cases_and_accept_rule():
+    """The accept rule of mathematics/intersection.py:42-65 and the tie rule of :106-116 /
+    core/scene.py:66-73 as known answers (no GPU): inclusive edges and vertices, inclusive t range,
+    lowest id on exact ties, no back-face culling, degenerate triangles never hit, empty inputs."""
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], np.float32)
+    # empty scene / zero rays
+    ids, t, _, _ = oracle.closest_hit(np.zeros((0, 3, 3), np.float32), _rays([[0, 0, 1]], [[0, 0, -1]]))
+    assert ids.tolist() == [-1]
+    ids, _, _, _ = oracle.closest_hit(tri, np.zeros((0, 8), np.float32))
+    assert ids.shape == (0,)
+    assert oracle.any_hit(np.zeros((0, 3, 3), np.float32), _rays([[0, 0, 1]], [[0, 0, -1]])).tolist() == [0]
+    # interior, the three edges, the three vertices: all accepted (u, v >= 0, u + v <= 1 inclusive); from both sides
+    pts = [[0.25, 0.25], [0.5, 0.0], [0.0, 0.5], [0.5, 0.5], [0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]
+    for z, dz in ((1.0, -1.0), (-1.0, 1.0)):
+        r = _rays([[x, y, z] for x, y in pts], [[0, 0, dz]] * len(pts))
+        ids, t, u, v = oracle.closest_hit(tri, r)
+        assert ids.tolist() == [0] * len(pts) and np.allclose(t, 1.0)
+        assert np.allclose(u, [p[0] for p in pts]) and np.allclose(v, [p[1] for p in pts])
+    # just outside every edge: miss
+    r = _rays([[0.5, -1e-6, 1], [-1e-6, 0.5, 1], [0.5 + 1e-6, 0.5 + 1e-6, 1]], [[0, 0, -1]] * 3)
+    assert oracle.closest_hit(tri, r)[0].tolist() == [-1, -1, -1]
+    # t range is inclusive at both ends: tmin <= t <= tmax
+    r = _rays([[0.25, 0.25, 1.0]] * 4, [[0, 0, -1]] * 4)
+    r[:, 3] = [1.0, np.nextafter(np.float32(1.0), np.float32(2.0)), 0.0, 0.0]
+    r[:, 7] = [9.0, 9.0, 1.0, np.nextafter(np.float32(1.0), np.float32(0.0))]
+    assert oracle.closest_hit(tri, r)[0].tolist() == [0, -1, 0, -1]
+    # a ray in the triangle's plane (det == 0 up to the reference's EPS) and a ray pointing away: miss
+    r = _rays([[-1, 0.25, 0.0], [0.25, 0.25, 1.0]], [[1, 0, 0], [0, 0, 1]])
+    assert oracle.closest_hit(tri, r)[0].tolist() == [-1, -1]
+    # degenerate triangles (point, segment) are never hit
+    deg = np.array([[[0.2, 0.2, 0]] * 3, [[0, 0, 0], [1, 0, 0], [1, 0, 0]]], np.float32)
+    r = _rays([[0.2, 0.2, 1], [0.5, 0.0, 1]], [[0, 0, -1]] * 2)
+    assert oracle.closest_hit(deg, r)[0].tolist() == [-1, -1]
+    # exact ties: identical triangles -> the lowest id, whatever the order they are stored in; closest = min t
+    stack = np.concatenate([tri + np.float32([0, 0, -1]), tri, tri, tri + np.float32([0, 0, 0.5]), tri + np.float32([0, 0, 0.5])])
+    r = _rays([[0.25, 0.25, 2.0], [0.25, 0.25, 0.25], [0.25, 0.25, -3.0]], [[0, 0, -1], [0, 0, -1], [0, 0, 1]])
+    ids, t, _, _ = oracle.closest_hit(stack, r)
+    assert ids.tolist() == [3, 1, 0] and np.allclose(t, [1.5, 0.25, 2.0])
+    cnt, sums = oracle.all_hits(stack, r)
+    K = 0x9E3779B97F4A7C15  # the hit SET: every triangle on the line; checksum = sum((id + 1) * K) mod 2^64
+    assert cnt.tolist() == [5, 3, 5]
+    assert sums.tolist() == [sum((i + 1) * K for i in s) % 2 ** 64 for s in ((0, 1, 2, 3, 4), (0, 1, 2), (0, 1, 2, 3, 4))]
+    assert oracle.any_hit(stack, r).tolist() == [1, 1, 1]
+    # a shared edge between two triangles of a quad: both contain the point, the lower id wins
+    quad = np.array([[[0, 0, 0], [1, 0, 0], [1, 1, 0]], [[0, 0, 0], [1, 1, 0], [0, 1, 0]]], np.float32)
+    r = _rays([[0.5, 0.5, 1.0], [0.25, 0.25, 1.0]], [[0, 0, -1]] * 2)
+    assert oracle.closest_hit(quad, r)[0].tolist() == [0, 0]
+    assert oracle.closest_hit(quad[::-1].copy(), r)[0].tolist() == [0, 0]
+    assert oracle.all_hits(quad, r)[0].tolist() == [2, 2]
+
+
+def test_oracle_invariants_on_random_scenes():
+    """Size-independent properties of the restated algorithm: the grouped kernel equals the scalar one on every
+    (ray, triangle) pair it reports, a permutation of the triangles permutes the ids (no exact ties in a random
+    soup), any-hit == (closest id >= 0), the all-hits count bounds both, and a hit never leaves [tmin, tmax]."""
+    rng = np.random.default_rng(5)
+    nt, nr = 400, 3000
+    c = rng.uniform(0, 1, (nt, 1, 3))
+    tris = np.concatenate([c, c + rng.uniform(-0.1, 0.1, (nt, 2, 3))], 1).astype(np.float32)
+    d = rng.normal(size=(nr, 3))
+    rays = _rays(rng.uniform(0, 1, (nr, 3)), d / np.linalg.norm(d, axis=1, keepdims=True), tmin=1e-5, tmax=0.8)
+    ids, t, u, v = oracle.closest_hit(tris, rays)
+    hit = ids >= 0
+    assert 0.15 < hit.mean() < 1.0
+    assert np.all((t[hit] >= 1e-5) & (t[hit] <= np.float64(np.float32(0.8))))
+    assert np.all((u[hit] >= 0) & (v[hit] >= 0) & (u[hit] + v[hit] <= 1 + 1e-12))
+    perm = rng.permutation(nt)
+    ids_p, t_p, _, _ = oracle.closest_hit(tris[perm], rays)
+    assert np.array_equal(np.where(ids_p >= 0, perm[np.maximum(ids_p, 0)], -1), ids) and np.array_equal(t_p, t)
+    occ = oracle.any_hit(tris, rays)
+    assert np.array_equal(occ.astype(bool), hit)
+    cnt, sums = oracle.all_hits(tris, rays)
+    K = np.uint64(0x9E3779B97F4A7C15)
+    assert np.all((cnt > 0) == hit) and np.all(sums[cnt == 1] == (ids[cnt == 1].astype(np.uint64) + np.uint64(1)) * K)
+    for k in np.nonzero(hit)[0][:200]:  # scalar kernel (intersection.py:7-39) on the reported pairs
+        ok, ts = oracle.mt_scalar(*tris[ids[k]].astype(np.float64), rays[k, 0:3].astype(np.float64),
+                                  rays[k, 4:7].astype(np.float64), float(rays[k, 7]))
+        assert ok and abs(ts - t[k]) <= 1e-12 * max(1.0, abs(t[k]))
